@@ -1,0 +1,434 @@
+// snap_api.cu -- planner + C ABI of libnvrx_snap.so (see include/nvrx_snap.h for the contract and the
+// reference file:line each entry point replaces).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "nvrx_snap.h"
+#include "snap_kernels.cuh"
+
+using nvrx::PeerMap;
+using nvrx::SegDesc;
+using nvrx::TileDesc;
+
+#define NVRX_CUDA(expr)                                   \
+    do {                                                  \
+        cudaError_t e__ = (expr);                         \
+        if (e__ != cudaSuccess) return static_cast<int>(e__); \
+    } while (0)
+
+namespace {
+
+constexpr uint64_t kDefaultAlign = 512;
+constexpr uint32_t kDefaultTile = 32768;
+constexpr uint32_t kMinBulkBytes = 1024;  // smaller aligned pieces are cheaper on the ragged warps
+
+inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+inline bool is_pow2(uint64_t v) { return v && !(v & (v - 1)); }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess) {
+            ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+            if (prev == dev) prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct nvrx_plan {
+    int device = 0;
+    int sm_count = 0;
+    int64_t n = 0;
+    uint64_t align = kDefaultAlign;
+    uint32_t tile_bytes = kDefaultTile;
+    int variant = NVRX_VARIANT_AUTO;
+    bool any_narrow = false;
+
+    std::vector<uint64_t> ptrs, nbytes, off, packed;
+    std::vector<uint32_t> flags;
+    uint64_t staging_bytes = 0;
+    uint64_t algo_bytes = 0;
+
+    // sharding of the packed range for the fused exchange (0 = none)
+    uint64_t shard_bytes = 0;
+
+    // descriptor tables: host mirror (pinned) and device copy
+    SegDesc* h_segs = nullptr;
+    TileDesc* h_tiles = nullptr;
+    SegDesc* d_segs = nullptr;
+    TileDesc* d_tiles = nullptr;
+    size_t tiles_cap = 0;  // capacity (entries) of h_tiles / d_tiles
+    uint32_t n_bulk = 0, n_tiles = 0;
+    bool segs_dirty = true, tiles_dirty = true;
+};
+
+namespace {
+
+// Build the tile list: tiles[0,n_bulk) are TMA-eligible, the rest ragged.  Both are emitted in segment
+// order so that neighbouring CTAs touch neighbouring DRAM pages.
+int build_tiles(nvrx_plan* p) {
+    std::vector<TileDesc> bulk, ragged;
+    const uint32_t T = p->tile_bytes;
+    size_t est = 0;
+    for (int64_t i = 0; i < p->n; ++i) est += static_cast<size_t>(p->nbytes[i] / T + 2);
+    bulk.reserve(est);
+    for (int64_t i = 0; i < p->n; ++i) {
+        const uint64_t nb = p->nbytes[i];
+        if (nb == 0) continue;
+        const bool narrow = (p->flags[i] & NVRX_SEG_NARROW_F32_BF16) != 0;
+        const bool ptr_al = (p->ptrs[i] & 15u) == 0;
+        const uint64_t scale = narrow ? 2 : 1;  // tensor bytes per staging byte
+        uint64_t o = 0;
+        while (o < nb) {
+            uint64_t len = std::min<uint64_t>(T, nb - o);
+            if (p->shard_bytes) {
+                // never let a tile straddle a shard boundary of the packed range
+                const uint64_t pos = p->off[i] + o / scale;
+                const uint64_t room = (p->shard_bytes - pos % p->shard_bytes) * scale;
+                len = std::min(len, room);
+            }
+            TileDesc td;
+            td.seg = static_cast<uint32_t>(i);
+            td.off = o;
+            if (!narrow && ptr_al && len >= kMinBulkBytes) {
+                const uint32_t body = static_cast<uint32_t>(len & ~uint64_t(15));
+                td.nbytes = body;
+                bulk.push_back(td);
+                if (len > body) {
+                    td.off = o + body;
+                    td.nbytes = static_cast<uint32_t>(len - body);
+                    ragged.push_back(td);
+                }
+            } else {
+                td.nbytes = static_cast<uint32_t>(len);
+                ragged.push_back(td);
+            }
+            o += len;
+        }
+    }
+    const size_t total = bulk.size() + ragged.size();
+    if (total > 0xffffffffull) return NVRX_E_INVALID;
+    if (total > p->tiles_cap) {
+        const size_t cap = std::max<size_t>(total + total / 8, 64);
+        if (p->h_tiles) cudaFreeHost(p->h_tiles);
+        if (p->d_tiles) cudaFree(p->d_tiles);
+        p->h_tiles = nullptr;
+        p->d_tiles = nullptr;
+        p->tiles_cap = 0;
+        NVRX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_tiles), cap * sizeof(TileDesc)));
+        NVRX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_tiles), cap * sizeof(TileDesc)));
+        p->tiles_cap = cap;
+    }
+    if (!bulk.empty()) memcpy(p->h_tiles, bulk.data(), bulk.size() * sizeof(TileDesc));
+    if (!ragged.empty()) memcpy(p->h_tiles + bulk.size(), ragged.data(), ragged.size() * sizeof(TileDesc));
+    p->n_bulk = static_cast<uint32_t>(bulk.size());
+    p->n_tiles = static_cast<uint32_t>(total);
+    p->tiles_dirty = true;
+    return NVRX_OK;
+}
+
+void fill_segs(nvrx_plan* p) {
+    for (int64_t i = 0; i < p->n; ++i) {
+        SegDesc& s = p->h_segs[i];
+        s.ptr = p->ptrs[i];
+        s.stg_off = p->off[i];
+        s.nbytes = p->nbytes[i];
+        s.flags = p->flags[i];
+        s.pad = 0;
+    }
+    p->segs_dirty = true;
+}
+
+int upload(nvrx_plan* p, cudaStream_t st) {
+    if (p->segs_dirty && p->n > 0) {
+        NVRX_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, static_cast<size_t>(p->n) * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+    }
+    p->segs_dirty = false;
+    if (p->tiles_dirty && p->n_tiles > 0) {
+        NVRX_CUDA(cudaMemcpyAsync(p->d_tiles, p->h_tiles, static_cast<size_t>(p->n_tiles) * sizeof(TileDesc),
+                                  cudaMemcpyHostToDevice, st));
+    }
+    p->tiles_dirty = false;
+    return NVRX_OK;
+}
+
+// ring geometry of the TMA walker: STAGES smem slots of tile_bytes, LOADS tiles of loads in flight.
+// The deepest ring that fits the 227 KB of shared memory is chosen unless NVRX_B200_TMA_STAGES overrides it.
+constexpr size_t kSmemBudget = 200 * 1024;
+
+int pick_stages(uint32_t tile_bytes) {
+    // measured on B200, 16 GB Llama-shaped state (profiles/r01_selftest_sweep.log): 32 KiB x 4 stages x 1 CTA/SM
+    // is the fastest ring (6.49 TB/s algorithmic); 16 KiB x 6 x 2 CTAs/SM and 64 KiB x 3 are within 2 %.
+    static const int kChoices[] = {12, 8, 6, 4, 3};
+    int want = tile_bytes >= 65536 ? 3 : tile_bytes >= 32768 ? 4 : tile_bytes >= 16384 ? 6 : 12;
+    if (const char* env = getenv("NVRX_B200_TMA_STAGES")) want = atoi(env);
+    for (int c : kChoices) {
+        if (static_cast<size_t>(c) * tile_bytes > kSmemBudget) continue;
+        if (c <= want) return c;
+    }
+    return 3;
+}
+
+template <int DIR, int STAGES, int LOADS>
+int launch_tma(nvrx_plan* p, uint8_t* staging, const PeerMap& pm, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(STAGES) * p->tile_bytes;
+    auto kern = nvrx::walk_tma<DIR, STAGES, LOADS>;
+    NVRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    uint32_t per_sm = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 2048))));
+    if (const char* env = getenv("NVRX_B200_TMA_CTAS_PER_SM")) per_sm = std::max(1, atoi(env));
+    uint32_t grid = static_cast<uint32_t>(p->sm_count) * per_sm;
+    const uint32_t need = std::max<uint32_t>(p->n_bulk, (p->n_tiles - p->n_bulk + 2) / 3);
+    grid = std::max<uint32_t>(1, std::min(grid, need));
+    kern<<<grid, nvrx::kTmaThreads, smem, st>>>(p->d_segs, p->d_tiles, p->n_bulk, p->n_tiles, staging, p->tile_bytes, pm);
+    NVRX_CUDA(cudaGetLastError());
+    return NVRX_OK;
+}
+
+template <int DIR>
+int launch(nvrx_plan* p, uint8_t* staging, const PeerMap& pm, cudaStream_t st) {
+    if (p->n_tiles == 0) return NVRX_OK;
+    int variant = p->variant;
+    if (variant == NVRX_VARIANT_AUTO) variant = (p->any_narrow || p->n_bulk == 0) ? NVRX_VARIANT_LDG : NVRX_VARIANT_TMA;
+    if (variant == NVRX_VARIANT_TMA) {
+        switch (pick_stages(p->tile_bytes)) {
+            case 12: return launch_tma<DIR, 12, 8>(p, staging, pm, st);
+            case 8: return launch_tma<DIR, 8, 6>(p, staging, pm, st);
+            case 6: return launch_tma<DIR, 6, 4>(p, staging, pm, st);
+            case 4: return launch_tma<DIR, 4, 3>(p, staging, pm, st);
+            default: return launch_tma<DIR, 3, 2>(p, staging, pm, st);
+        }
+    }
+    uint32_t per_sm = 4;
+    if (const char* env = getenv("NVRX_B200_LDG_CTAS_PER_SM")) per_sm = std::max(1, atoi(env));
+    uint32_t grid = static_cast<uint32_t>(p->sm_count) * per_sm;
+    grid = std::max<uint32_t>(1, std::min(grid, p->n_tiles));
+    nvrx::walk_ldg<DIR><<<grid, nvrx::kLdgThreads, 0, st>>>(p->d_segs, p->d_tiles, p->n_tiles, staging, pm);
+    NVRX_CUDA(cudaGetLastError());
+    return NVRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nvrx_abi_version(void) { return NVRX_ABI_VERSION; }
+
+const char* nvrx_strerror(int status) {
+    switch (status) {
+        case NVRX_OK: return "ok";
+        case NVRX_E_INVALID: return "nvrx: invalid argument";
+        case NVRX_E_NOMEM: return "nvrx: out of host memory";
+        case NVRX_E_STATE: return "nvrx: invalid state or timeout";
+        case NVRX_E_SYS: return "nvrx: operating-system call failed";
+        case NVRX_E_NODRIVER: return "nvrx: CUDA driver entry point unavailable";
+        default: break;
+    }
+    if (status > 0 && status < 1000) return cudaGetErrorString(static_cast<cudaError_t>(status));
+    return "nvrx: unknown status";
+}
+
+int nvrx_device_info(int device, int* sm_count, uint64_t* l2_bytes, char* name, int name_len) {
+    cudaDeviceProp prop;
+    NVRX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = static_cast<uint64_t>(prop.l2CacheSize);
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, static_cast<size_t>(name_len) - 1);
+        name[name_len - 1] = 0;
+    }
+    return NVRX_OK;
+}
+
+int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes, const uint32_t* flags, uint64_t align,
+                     uint32_t tile_bytes, int device, nvrx_plan** out) {
+    if (!out || n < 0 || (n > 0 && (!ptrs || !nbytes))) return NVRX_E_INVALID;
+    if (align == 0) align = kDefaultAlign;
+    if (tile_bytes == 0) tile_bytes = kDefaultTile;
+    if (!is_pow2(align) || align < 16) return NVRX_E_INVALID;
+    if (!is_pow2(tile_bytes) || tile_bytes < 4096 || tile_bytes > 65536) return NVRX_E_INVALID;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t f = flags ? flags[i] : 0;
+        if (nbytes[i] && !ptrs[i]) return NVRX_E_INVALID;
+        if (f & ~NVRX_SEG_NARROW_F32_BF16) return NVRX_E_INVALID;
+        if ((f & NVRX_SEG_NARROW_F32_BF16) && ((nbytes[i] & 3u) || (reinterpret_cast<uintptr_t>(ptrs[i]) & 3u)))
+            return NVRX_E_INVALID;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return static_cast<int>(cudaErrorInvalidDevice);
+
+    nvrx_plan* p = new (std::nothrow) nvrx_plan();
+    if (!p) return NVRX_E_NOMEM;
+    p->device = device;
+    p->n = n;
+    p->align = align;
+    p->tile_bytes = tile_bytes;
+    int rc = static_cast<int>(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    p->ptrs.resize(n);
+    p->nbytes.assign(nbytes, nbytes + n);
+    p->flags.resize(n);
+    p->off.resize(n);
+    p->packed.resize(n);
+    uint64_t cur = 0, src_total = 0, packed_total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        p->ptrs[i] = reinterpret_cast<uint64_t>(ptrs[i]);
+        p->flags[i] = flags ? flags[i] : 0;
+        const bool narrow = (p->flags[i] & NVRX_SEG_NARROW_F32_BF16) != 0;
+        p->any_narrow |= narrow;
+        p->packed[i] = narrow ? p->nbytes[i] / 2 : p->nbytes[i];
+        cur = round_up(cur, align);
+        p->off[i] = cur;
+        cur += p->packed[i];
+        src_total += p->nbytes[i];
+        packed_total += p->packed[i];
+    }
+    p->staging_bytes = round_up(cur, align);
+    p->algo_bytes = src_total + packed_total;
+
+    const size_t seg_cap = static_cast<size_t>(std::max<int64_t>(n, 1));
+    rc = static_cast<int>(cudaMallocHost(reinterpret_cast<void**>(&p->h_segs), seg_cap * sizeof(SegDesc)));
+    if (!rc) rc = static_cast<int>(cudaMalloc(reinterpret_cast<void**>(&p->d_segs), seg_cap * sizeof(SegDesc)));
+    if (!rc) {
+        fill_segs(p);
+        rc = build_tiles(p);
+    }
+    if (rc) {
+        nvrx_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return NVRX_OK;
+}
+
+int nvrx_plan_destroy(nvrx_plan* p) {
+    if (!p) return NVRX_OK;
+    DeviceGuard guard(p->device);
+    if (p->h_segs) cudaFreeHost(p->h_segs);
+    if (p->h_tiles) cudaFreeHost(p->h_tiles);
+    if (p->d_segs) cudaFree(p->d_segs);
+    if (p->d_tiles) cudaFree(p->d_tiles);
+    delete p;
+    return NVRX_OK;
+}
+
+int nvrx_plan_info(const nvrx_plan* p, uint64_t* staging_bytes, uint64_t* n_tiles, uint64_t* algorithmic_bytes) {
+    if (!p) return NVRX_E_INVALID;
+    if (staging_bytes) *staging_bytes = p->staging_bytes;
+    if (n_tiles) *n_tiles = p->n_tiles;
+    if (algorithmic_bytes) *algorithmic_bytes = p->algo_bytes;
+    return NVRX_OK;
+}
+
+int nvrx_plan_layout(const nvrx_plan* p, uint64_t* offsets, uint64_t* packed_nbytes) {
+    if (!p) return NVRX_E_INVALID;
+    for (int64_t i = 0; i < p->n; ++i) {
+        if (offsets) offsets[i] = p->off[i];
+        if (packed_nbytes) packed_nbytes[i] = p->packed[i];
+    }
+    return NVRX_OK;
+}
+
+int nvrx_plan_update_ptrs(nvrx_plan* p, const void* const* ptrs) {
+    if (!p || (p->n > 0 && !ptrs)) return NVRX_E_INVALID;
+    bool same_class = true;
+    for (int64_t i = 0; i < p->n; ++i) {
+        const uint64_t np = reinterpret_cast<uint64_t>(ptrs[i]);
+        if (p->nbytes[i] && !np) return NVRX_E_INVALID;
+        if ((p->flags[i] & NVRX_SEG_NARROW_F32_BF16) && (np & 3u)) return NVRX_E_INVALID;
+        if (((np ^ p->ptrs[i]) & 15u) != 0) same_class = false;
+    }
+    for (int64_t i = 0; i < p->n; ++i) p->ptrs[i] = reinterpret_cast<uint64_t>(ptrs[i]);
+    DeviceGuard guard(p->device);
+    fill_segs(p);
+    if (!same_class) return build_tiles(p);
+    return NVRX_OK;
+}
+
+int nvrx_plan_set_variant(nvrx_plan* p, int variant) {
+    if (!p || variant < NVRX_VARIANT_AUTO || variant > NVRX_VARIANT_TMA) return NVRX_E_INVALID;
+    p->variant = variant;
+    return NVRX_OK;
+}
+
+int nvrx_plan_commit(nvrx_plan* p, void* stream) {
+    if (!p) return NVRX_E_INVALID;
+    DeviceGuard guard(p->device);
+    return upload(p, static_cast<cudaStream_t>(stream));
+}
+
+int nvrx_pack(nvrx_plan* p, void* staging, void* stream) {
+    if (!p || (!staging && p->staging_bytes)) return NVRX_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(staging) & 511u) return NVRX_E_INVALID;
+    DeviceGuard guard(p->device);
+    if (p->shard_bytes) {
+        p->shard_bytes = 0;
+        int rc = build_tiles(p);
+        if (rc) return rc;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = upload(p, st);
+    if (rc) return rc;
+    PeerMap pm;
+    memset(&pm, 0, sizeof(pm));
+    return launch<nvrx::kDirPack>(p, static_cast<uint8_t*>(staging), pm, st);
+}
+
+int nvrx_scatter(nvrx_plan* p, const void* staging, void* stream) {
+    if (!p || (!staging && p->staging_bytes)) return NVRX_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(staging) & 511u) return NVRX_E_INVALID;
+    DeviceGuard guard(p->device);
+    if (p->shard_bytes) {
+        p->shard_bytes = 0;
+        int rc = build_tiles(p);
+        if (rc) return rc;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = upload(p, st);
+    if (rc) return rc;
+    PeerMap pm;
+    memset(&pm, 0, sizeof(pm));
+    return launch<nvrx::kDirScatter>(p, const_cast<uint8_t*>(static_cast<const uint8_t*>(staging)), pm, st);
+}
+
+int nvrx_pack_sharded(nvrx_plan* p, void* const* peer_bases, int n_peers, uint64_t shard_bytes, uint64_t slot_offset,
+                      void* stream) {
+    if (!p || !peer_bases || n_peers < 1 || n_peers > 16) return NVRX_E_INVALID;
+    if (shard_bytes == 0 || (shard_bytes & 511u) || (slot_offset & 511u)) return NVRX_E_INVALID;
+    if (shard_bytes * static_cast<uint64_t>(n_peers) < p->staging_bytes) return NVRX_E_INVALID;
+    DeviceGuard guard(p->device);
+    if (p->shard_bytes != shard_bytes) {
+        p->shard_bytes = shard_bytes;
+        int rc = build_tiles(p);
+        if (rc) return rc;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = upload(p, st);
+    if (rc) return rc;
+    PeerMap pm;
+    memset(&pm, 0, sizeof(pm));
+    pm.n_peers = n_peers;
+    pm.shard_bytes = shard_bytes;
+    pm.slot_off = slot_offset;
+    for (int j = 0; j < n_peers; ++j) {
+        if (!peer_bases[j] || (reinterpret_cast<uintptr_t>(peer_bases[j]) & 511u)) return NVRX_E_INVALID;
+        pm.bases[j] = static_cast<uint8_t*>(peer_bases[j]);
+    }
+    return launch<nvrx::kDirPack>(p, nullptr, pm, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,672 @@
+"""Host side of the B200 snapshot engine: thin objects over the C ABI plus the snapshot pipeline.
+
+Pipeline of one snapshot (``SnapshotEngine.snapshot``)::
+
+    tensors (HBM) --nvrx_pack (1 kernel, current stream)--> staging (HBM)
+                  --nvrx_drain (cudaMemcpyAsync, side stream)--> HostBuffer (pinned POSIX shm)
+                  --CPU-only writer process follows HostBuffer.progress--> file
+
+What it replaces in the reference (paths relative to ``src/nvidia_resiliency_ext/checkpointing``):
+
+* ``utils.py:85-99`` ``preload_tensors`` and ``local/basic_state_dict.py:162-174`` ``copy_tensors_to_cpu``:
+  N x (pinned allocation + ``cudaMemcpyAsync`` D2H) on the training stream, followed by a device-wide
+  ``torch.cuda.synchronize()`` (``async_ckpt/torch_ckpt.py:50``, ``local/ckpt_managers/base_manager.py:306-309``).
+  Here the training stream only carries the pack kernel; the D2H runs on a side stream.
+* ``local/basic_state_dict.py:176-187`` ``restore_tensor_device``: N blocking H2D copies -> one H2D + one
+  scatter kernel (``SnapshotEngine.restore``).
+
+There is no CPU fallback: everything here raises if ``libnvrx_snap.so`` or a CUDA device is missing.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+import uuid
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import SnapError, check
+
+DEFAULT_ALIGN = 512
+DEFAULT_DRAIN_CHUNK = 256 << 20
+
+
+def _ptr_array(values: Sequence[int]):
+    arr = (C.c_void_p * max(len(values), 1))()
+    for i, v in enumerate(values):
+        arr[i] = v
+    return arr
+
+
+def _u64_array(values: Sequence[int]):
+    return (C.c_uint64 * max(len(values), 1))(*values)
+
+
+def _u32_array(values: Sequence[int]):
+    return (C.c_uint32 * max(len(values), 1))(*values)
+
+
+class Plan:
+    """A compiled tensor table (``nvrx_plan``): segment layout in staging + tile work-list on the device."""
+
+    def __init__(
+        self,
+        ptrs: Sequence[int],
+        nbytes: Sequence[int],
+        flags: Optional[Sequence[int]] = None,
+        *,
+        device: int,
+        align: int = 0,
+        tile_bytes: int = 0,
+        variant: int = _cabi.VARIANT_AUTO,
+    ):
+        assert len(ptrs) == len(nbytes)
+        self._lib = _cabi.lib()
+        self.n = len(ptrs)
+        self.device = device
+        self._h = C.c_void_p()
+        flags_arr = _u32_array(flags) if flags is not None else None
+        check(
+            self._lib.nvrx_plan_create(
+                self.n, _ptr_array(ptrs), _u64_array(nbytes), flags_arr, align, tile_bytes, device, C.byref(self._h)
+            ),
+            "nvrx_plan_create",
+        )
+        stg, tiles, algo = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self._lib.nvrx_plan_info(self._h, C.byref(stg), C.byref(tiles), C.byref(algo)), "nvrx_plan_info")
+        self.staging_bytes = stg.value
+        self.algorithmic_bytes = algo.value
+        offs, packed = _u64_array([0] * self.n), _u64_array([0] * self.n)
+        check(self._lib.nvrx_plan_layout(self._h, offs, packed), "nvrx_plan_layout")
+        self.offsets: Tuple[int, ...] = tuple(offs[i] for i in range(self.n))
+        self.packed_nbytes: Tuple[int, ...] = tuple(packed[i] for i in range(self.n))
+        self.ptrs: Tuple[int, ...] = tuple(ptrs)
+        if variant != _cabi.VARIANT_AUTO:
+            self.set_variant(variant)
+
+    @property
+    def n_tiles(self) -> int:
+        tiles = C.c_uint64()
+        check(self._lib.nvrx_plan_info(self._h, None, C.byref(tiles), None), "nvrx_plan_info")
+        return tiles.value
+
+    def set_variant(self, variant: int) -> None:
+        check(self._lib.nvrx_plan_set_variant(self._h, variant), "nvrx_plan_set_variant")
+
+    def update_ptrs(self, ptrs: Sequence[int]) -> None:
+        assert len(ptrs) == self.n
+        if tuple(ptrs) == self.ptrs:
+            return
+        check(self._lib.nvrx_plan_update_ptrs(self._h, _ptr_array(ptrs)), "nvrx_plan_update_ptrs")
+        self.ptrs = tuple(ptrs)
+
+    def commit(self, stream: int) -> None:
+        check(self._lib.nvrx_plan_commit(self._h, stream), "nvrx_plan_commit")
+
+    def pack(self, staging_ptr: int, stream: int) -> None:
+        check(self._lib.nvrx_pack(self._h, staging_ptr, stream), "nvrx_pack")
+
+    def scatter(self, staging_ptr: int, stream: int) -> None:
+        check(self._lib.nvrx_scatter(self._h, staging_ptr, stream), "nvrx_scatter")
+
+    def pack_sharded(self, peer_bases: Sequence[int], shard_bytes: int, slot_offset: int, stream: int) -> None:
+        check(
+            self._lib.nvrx_pack_sharded(
+                self._h, _ptr_array(peer_bases), len(peer_bases), shard_bytes, slot_offset, stream
+            ),
+            "nvrx_pack_sharded",
+        )
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.nvrx_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBuffer:
+    """cudaMalloc'ed, zero-filled, IPC-exportable device memory (``nvrx_dev_alloc``)."""
+
+    def __init__(self, nbytes: int, device: int):
+        self._lib = _cabi.lib()
+        self.device = device
+        self.nbytes = nbytes
+        p = C.c_void_p()
+        check(self._lib.nvrx_dev_alloc(device, nbytes, C.byref(p)), "nvrx_dev_alloc")
+        self.ptr = p.value
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self._lib.nvrx_ipc_export(self.ptr, buf), "nvrx_ipc_export")
+        return buf.raw
+
+    def close(self) -> None:
+        if self.ptr:
+            self._lib.nvrx_dev_free(self.device, self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Stream:
+    def __init__(self, device: int, high_priority: bool = False):
+        self._lib = _cabi.lib()
+        p = C.c_void_p()
+        check(self._lib.nvrx_stream_create(device, int(high_priority), C.byref(p)), "nvrx_stream_create")
+        self.handle = p.value
+
+    def synchronize(self) -> None:
+        check(self._lib.nvrx_stream_sync(self.handle), "nvrx_stream_sync")
+
+    def wait_event(self, ev: "Event") -> None:
+        check(self._lib.nvrx_stream_wait_event(self.handle, ev.handle), "nvrx_stream_wait_event")
+
+    def close(self) -> None:
+        if self.handle:
+            self._lib.nvrx_stream_destroy(self.handle)
+            self.handle = 0
+
+
+class Event:
+    def __init__(self, device: int, timing: bool = False):
+        self._lib = _cabi.lib()
+        p = C.c_void_p()
+        check(self._lib.nvrx_event_create(device, int(timing), C.byref(p)), "nvrx_event_create")
+        self.handle = p.value
+
+    def record(self, stream: int) -> None:
+        check(self._lib.nvrx_event_record(self.handle, stream), "nvrx_event_record")
+
+    def query(self) -> bool:
+        done = C.c_int()
+        check(self._lib.nvrx_event_query(self.handle, C.byref(done)), "nvrx_event_query")
+        return bool(done.value)
+
+    def synchronize(self) -> None:
+        check(self._lib.nvrx_event_sync(self.handle), "nvrx_event_sync")
+
+    def elapsed_ms(self, end: "Event") -> float:
+        ms = C.c_float()
+        check(self._lib.nvrx_event_elapsed_ms(self.handle, end.handle, C.byref(ms)), "nvrx_event_elapsed_ms")
+        return ms.value
+
+    def close(self) -> None:
+        if self.handle:
+            self._lib.nvrx_event_destroy(self.handle)
+            self.handle = 0
+
+
+def stream_wait_event(stream: int, ev: Event) -> None:
+    check(_cabi.lib().nvrx_stream_wait_event(stream, ev.handle), "nvrx_stream_wait_event")
+
+
+class HostBuffer:
+    """One snapshot slot in host memory: a POSIX shm mapping with a progress word, optionally pinned."""
+
+    def __init__(self, handle: int, name: Optional[str], owner: bool):
+        self._lib = _cabi.lib()
+        self._h = C.c_void_p(handle)
+        self.name = name
+        self.owner = owner
+        self.data_ptr: int = self._lib.nvrx_hostbuf_data(self._h)
+        self.capacity: int = self._lib.nvrx_hostbuf_capacity(self._h)
+        self.progress_ptr: int = self._lib.nvrx_hostbuf_progress(self._h)
+
+    @classmethod
+    def create(
+        cls, nbytes: int, *, name: Optional[str] = None, pin: bool = True, device: int = 0, prefault_threads: int = 0
+    ) -> "HostBuffer":
+        h = C.c_void_p()
+        cname = name.encode() if name else None
+        check(
+            _cabi.lib().nvrx_hostbuf_create(cname, nbytes, prefault_threads, int(pin), device, C.byref(h)),
+            "nvrx_hostbuf_create",
+        )
+        return cls(h.value, name, owner=True)
+
+    @classmethod
+    def open(cls, name: str) -> "HostBuffer":
+        h = C.c_void_p()
+        check(_cabi.lib().nvrx_hostbuf_open(name.encode(), C.byref(h)), "nvrx_hostbuf_open")
+        return cls(h.value, name, owner=False)
+
+    @property
+    def progress(self) -> int:
+        return C.c_uint64.from_address(self.progress_ptr).value
+
+    def wait(self, value: int, timeout_ms: int = -1) -> None:
+        check(self._lib.nvrx_hostbuf_wait(self._h, value, timeout_ms), "nvrx_hostbuf_wait")
+
+    def as_tensor(self, nbytes: Optional[int] = None) -> torch.Tensor:
+        """uint8 tensor over the first ``nbytes`` of the payload (default: all of it), no copy.
+
+        The tensor's *storage* is exactly ``nbytes`` long, so ``torch.save`` of views into it writes the
+        snapshot and not the slot's spare capacity.  The mapping must outlive the tensor."""
+        nbytes = self.capacity if nbytes is None else nbytes
+        assert 0 <= nbytes <= self.capacity
+        if nbytes == 0:
+            return torch.empty(0, dtype=torch.uint8)
+        raw = (C.c_uint8 * nbytes).from_address(self.data_ptr)
+        t = torch.frombuffer(raw, dtype=torch.uint8)
+        t._nvrx_hostbuf = self  # keep this object (not the mapping!) alive with the base tensor
+        return t
+
+    def write_fd(self, offset: int, nbytes: int, fd: int, file_off: int, threads: int = 8) -> None:
+        check(self._lib.nvrx_hostbuf_write_fd(self._h, offset, nbytes, fd, file_off, threads), "nvrx_hostbuf_write_fd")
+
+    def crc32(self, offset: int, nbytes: int, threads: int = 8) -> int:
+        out = C.c_uint32()
+        check(self._lib.nvrx_hostbuf_crc32(self._h, offset, nbytes, threads, C.byref(out)), "nvrx_hostbuf_crc32")
+        return out.value
+
+    def close(self, unlink: Optional[bool] = None) -> None:
+        if self._h:
+            self._lib.nvrx_hostbuf_destroy(self._h, int(self.owner if unlink is None else unlink))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------------
+# layout description that travels to writer processes / into checkpoint files
+# --------------------------------------------------------------------------------------------------
+_DTYPE_NAMES = {
+    str(d).replace("torch.", ""): d
+    for d in (
+        torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int8, torch.uint8, torch.int16,
+        torch.int32, torch.int64, torch.bool, torch.complex64, torch.complex128,
+    )
+}
+for _extra in ("float8_e4m3fn", "float8_e5m2", "uint16", "uint32", "uint64"):
+    if hasattr(torch, _extra):
+        _DTYPE_NAMES[_extra] = getattr(torch, _extra)
+
+
+def dtype_name(dtype: torch.dtype) -> str:
+    return str(dtype).replace("torch.", "")
+
+
+@dataclass
+class PackedLayout:
+    """Where every tensor of a flattened state dict lives inside a packed buffer."""
+
+    shapes: List[Tuple[int, ...]]
+    dtypes: List[str]  # dtype of the *packed* data (bf16 for narrowed fp32 tensors)
+    src_dtypes: List[str]  # dtype of the tensor on the device
+    offsets: List[int]
+    packed_nbytes: List[int]
+    total_bytes: int
+    align: int = DEFAULT_ALIGN
+
+    def views(self, buf: torch.Tensor) -> List[torch.Tensor]:
+        """Typed tensor views into a uint8 buffer holding the packed bytes."""
+        out = []
+        for shape, dt, off, nb in zip(self.shapes, self.dtypes, self.offsets, self.packed_nbytes):
+            dtype = _DTYPE_NAMES[dt]
+            if nb == 0:
+                out.append(torch.empty(shape, dtype=dtype, device=buf.device))
+            else:
+                out.append(buf[off : off + nb].view(dtype).view(shape))
+        return out
+
+
+def expected_layout(nbytes: Sequence[int], narrow: Sequence[bool], align: int = DEFAULT_ALIGN) -> Tuple[List[int], List[int], int]:
+    """Pure-Python statement of the layout rule in include/nvrx_snap.h (used for cross-checks only)."""
+    offs, packed, cur = [], [], 0
+    for nb, nr in zip(nbytes, narrow):
+        cur = (cur + align - 1) // align * align
+        offs.append(cur)
+        pk = nb // 2 if nr else nb
+        packed.append(pk)
+        cur += pk
+    return offs, packed, (cur + align - 1) // align * align
+
+
+# --------------------------------------------------------------------------------------------------
+# the pipeline
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class _Slot:
+    index: int
+    buf: Optional[HostBuffer] = None
+    busy: bool = False
+    drained_total: int = 0  # cumulative bytes the progress word has been advanced by
+    done_event: Optional[Event] = None
+
+
+@dataclass
+class Snapshot:
+    """Handle of one in-flight / completed snapshot."""
+
+    engine: "SnapshotEngine"
+    slot: _Slot
+    layout: PackedLayout
+    progress_target: int
+    passthrough: Dict[int, torch.Tensor] = field(default_factory=dict)  # position -> non-CUDA tensor kept as is
+    n_total: int = 0
+    pack_start: Optional[Event] = None
+    pack_stop: Optional[Event] = None
+    released: bool = False
+
+    def drained(self) -> bool:
+        return self.slot.done_event.query()
+
+    def wait(self) -> None:
+        """Block the calling CPU thread until the bytes are in host memory (no device-wide sync)."""
+        self.slot.done_event.synchronize()
+
+    def host_views(self) -> List[torch.Tensor]:
+        """CPU tensor views (one per input tensor, input order) into the pinned shm slot.
+
+        Their *content* is valid once :meth:`wait` returned / ``drained()`` is true -- same contract as the
+        reference's ``tensor.to("cpu", non_blocking=True)`` before ``torch.cuda.synchronize()``."""
+        packed = self.layout.views(self.slot.buf.as_tensor(self.layout.total_bytes))
+        if not self.passthrough:
+            return packed
+        out, it = [], iter(packed)
+        for i in range(self.n_total):
+            out.append(self.passthrough[i] if i in self.passthrough else next(it))
+        return out
+
+    def pack_ms(self) -> float:
+        self.pack_stop.synchronize()
+        return self.pack_start.elapsed_ms(self.pack_stop)
+
+    def descriptor(self) -> dict:
+        """Picklable description a CPU-only process needs to follow and read this snapshot."""
+        return {
+            "shm_name": self.slot.buf.name,
+            "progress_target": self.progress_target,
+            "layout": self.layout,
+        }
+
+    def release(self) -> None:
+        if not self.released:
+            self.released = True
+            self.engine._release(self.slot)
+
+
+class SnapshotEngine:
+    """Per-(process, device) snapshot engine.  Thread-compatible: call from the training thread."""
+
+    _instances: Dict[int, "SnapshotEngine"] = {}
+    _lock = threading.Lock()
+
+    def __init__(
+        self,
+        device: Optional[int] = None,
+        *,
+        host_slots: int = 2,
+        align: int = DEFAULT_ALIGN,
+        tile_bytes: int = 0,
+        variant: Optional[int] = None,
+        drain_chunk: int = DEFAULT_DRAIN_CHUNK,
+        shm_prefix: Optional[str] = None,
+        timing: bool = False,
+        prefault_threads: Optional[int] = None,
+    ):
+        if not torch.cuda.is_available():
+            raise SnapError(_cabi.E_STATE, "SnapshotEngine", "no CUDA device - the snapshot path has no CPU fallback")
+        self.lib = _cabi.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.align = align
+        self.tile_bytes = tile_bytes or int(os.environ.get("NVRX_B200_TILE_BYTES", "0"))
+        if variant is None:
+            variant = {"auto": 0, "ldg": 1, "tma": 2}[os.environ.get("NVRX_B200_VARIANT", "auto").lower()]
+        self.variant = variant
+        self.drain_chunk = drain_chunk
+        self.timing = timing
+        self.prefault_threads = prefault_threads if prefault_threads is not None else min(16, os.cpu_count() or 1)
+        self.shm_prefix = shm_prefix or f"/nvrx_b200_{os.getpid()}_{uuid.uuid4().hex[:8]}"
+        self._plans: Dict[tuple, Plan] = {}
+        self._staging: Optional[DeviceBuffer] = None
+        self._staging_free: Optional[Event] = None  # recorded when the last reader of staging finished
+        self._side = Stream(self.device)
+        self._slots = [_Slot(i) for i in range(max(1, host_slots))]
+        self._slot_gen = 0
+        self.launches = 0  # kernels launched by this engine (pack + scatter)
+
+    # ---- singletons per device ------------------------------------------------------------------
+    @classmethod
+    def get(cls, device: Optional[int] = None, **kwargs) -> "SnapshotEngine":
+        dev = torch.cuda.current_device() if device is None else int(device)
+        with cls._lock:
+            eng = cls._instances.get(dev)
+            if eng is None:
+                eng = cls(dev, **kwargs)
+                cls._instances[dev] = eng
+            return eng
+
+    @classmethod
+    def shutdown_all(cls) -> None:
+        with cls._lock:
+            for eng in cls._instances.values():
+                eng.close()
+            cls._instances.clear()
+
+    # ---- resources ------------------------------------------------------------------------------
+    def _current_stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ensure_staging(self, nbytes: int) -> DeviceBuffer:
+        if self._staging is None or self._staging.nbytes < nbytes:
+            if self._staging is not None:
+                if self._staging_free is not None:
+                    self._staging_free.synchronize()
+                self._staging.close()
+            self._staging = DeviceBuffer(max(nbytes, 512), self.device)
+        return self._staging
+
+    def _acquire_slot(self, nbytes: int) -> _Slot:
+        slot = next((s for s in self._slots if not s.busy), None)
+        if slot is None:
+            raise SnapError(
+                _cabi.E_STATE,
+                "acquiring a host snapshot slot",
+                f"all {len(self._slots)} slots hold unfinalized snapshots; finalize earlier saves first "
+                "(or raise host_slots)",
+            )
+        if slot.buf is None or slot.buf.capacity < nbytes:
+            if slot.buf is not None:
+                slot.buf.close()
+            self._slot_gen += 1
+            name = f"{self.shm_prefix}_s{slot.index}_g{self._slot_gen}"
+            slot.buf = HostBuffer.create(
+                nbytes, name=name, pin=True, device=self.device, prefault_threads=self.prefault_threads
+            )
+            slot.drained_total = 0
+        if slot.done_event is None:
+            slot.done_event = Event(self.device)
+        slot.busy = True
+        return slot
+
+    def _release(self, slot: _Slot) -> None:
+        slot.busy = False
+
+    def reserve(self, nbytes: int) -> None:
+        """Pre-allocate staging and every host slot for snapshots of up to ``nbytes`` packed bytes (pinning
+        16 GB takes seconds; do it once at start-up instead of inside the first save)."""
+        self._ensure_staging(nbytes)
+        for s in self._slots:
+            if not s.busy:
+                self._acquire_slot(nbytes)
+                self._release(s)
+
+    # ---- planning -------------------------------------------------------------------------------
+    def _plan_for(self, tensors: Sequence[torch.Tensor], narrow: Sequence[bool]) -> Plan:
+        key = tuple((t.numel() * t.element_size(), t.dtype, nr) for t, nr in zip(tensors, narrow))
+        ptrs = [t.data_ptr() if t.numel() else 0 for t in tensors]
+        plan = self._plans.get(key)
+        if plan is None:
+            nbytes = [k[0] for k in key]
+            flags = [_cabi.SEG_NARROW_F32_BF16 if nr else 0 for nr in narrow]
+            plan = Plan(
+                ptrs, nbytes, flags, device=self.device, align=self.align, tile_bytes=self.tile_bytes,
+                variant=self.variant,
+            )
+            self._plans[key] = plan
+        else:
+            plan.update_ptrs(ptrs)
+        return plan
+
+    @staticmethod
+    def _narrow_mask(tensors: Sequence[torch.Tensor], narrow: bool) -> List[bool]:
+        return [bool(narrow) and t.dtype == torch.float32 and t.numel() > 0 for t in tensors]
+
+    # ---- snapshot -------------------------------------------------------------------------------
+    def snapshot(self, tensors: Sequence[torch.Tensor], *, narrow: bool = False) -> Snapshot:
+        """Pack ``tensors`` (CUDA tensors of this device; others pass through) and start the drain.
+
+        Returns as soon as the pack kernel and the side-stream copy are *enqueued*."""
+        all_tensors = list(tensors)
+        passthrough = {i: t for i, t in enumerate(all_tensors) if not (t.is_cuda and t.device.index == self.device)}
+        cuda_tensors = [t.detach() for i, t in enumerate(all_tensors) if i not in passthrough]
+        # the kernel walks contiguous byte ranges; strided tensors are compacted first (rare)
+        cuda_tensors = [t if t.is_contiguous() else t.contiguous() for t in cuda_tensors]
+        mask = self._narrow_mask(cuda_tensors, narrow)
+        plan = self._plan_for(cuda_tensors, mask)
+
+        stream = self._current_stream()
+        staging = self._ensure_staging(plan.staging_bytes)
+        slot = self._acquire_slot(plan.staging_bytes)
+        if self._staging_free is not None:
+            # the previous drain may still be reading staging: order the pack after it on the GPU
+            stream_wait_event(stream, self._staging_free)
+
+        start = stop = None
+        if self.timing:
+            start, stop = Event(self.device, timing=True), Event(self.device, timing=True)
+            plan.commit(stream)
+            start.record(stream)
+        plan.pack(staging.ptr, stream)
+        self.launches += 1 if plan.n_tiles else 0
+        packed = stop if stop is not None else Event(self.device)
+        packed.record(stream)
+
+        self._side.wait_event(packed)
+        base = slot.drained_total
+        check(
+            self.lib.nvrx_drain(
+                slot.buf.data_ptr, staging.ptr, plan.staging_bytes, self.drain_chunk, slot.buf.progress_ptr, base,
+                self._side.handle, slot.done_event.handle,
+            ),
+            "nvrx_drain",
+        )
+        slot.drained_total = base + plan.staging_bytes
+        self._staging_free = slot.done_event
+
+        layout = PackedLayout(
+            shapes=[tuple(t.shape) for t in cuda_tensors],
+            dtypes=[dtype_name(torch.bfloat16 if nr else t.dtype) for t, nr in zip(cuda_tensors, mask)],
+            src_dtypes=[dtype_name(t.dtype) for t in cuda_tensors],
+            offsets=list(plan.offsets),
+            packed_nbytes=list(plan.packed_nbytes),
+            total_bytes=plan.staging_bytes,
+            align=self.align,
+        )
+        return Snapshot(
+            engine=self, slot=slot, layout=layout, progress_target=slot.drained_total, passthrough=passthrough,
+            n_total=len(all_tensors), pack_start=start, pack_stop=stop,
+        )
+
+    # ---- restore --------------------------------------------------------------------------------
+    def restore(
+        self,
+        host_tensors: Sequence[torch.Tensor],
+        *,
+        widen_to: Optional[Sequence[torch.dtype]] = None,
+        out: Optional[Sequence[torch.Tensor]] = None,
+    ) -> List[torch.Tensor]:
+        """CPU tensors -> CUDA tensors of this device with one H2D copy and one scatter kernel.
+
+        ``widen_to[i] == torch.float32`` for a bf16 host tensor widens it in the scatter kernel (exact)."""
+        host_tensors = [t.detach() for t in host_tensors]
+        target_dtypes = [
+            (widen_to[i] if widen_to is not None and widen_to[i] is not None else t.dtype)
+            for i, t in enumerate(host_tensors)
+        ]
+        mask = [td == torch.float32 and t.dtype == torch.bfloat16 and t.numel() > 0 for t, td in zip(host_tensors, target_dtypes)]
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            out = [torch.empty(t.shape, dtype=td, device=dev) for t, td in zip(host_tensors, target_dtypes)]
+        else:
+            out = list(out)
+            for o, t, td in zip(out, host_tensors, target_dtypes):
+                assert o.is_cuda and o.is_contiguous() and o.dtype == td and o.shape == t.shape
+        plan = self._plan_for(out, mask)
+        staging = self._ensure_staging(plan.staging_bytes)
+        slot = self._acquire_slot(plan.staging_bytes)
+        try:
+            # gather the CPU tensors into the pinned slot at the plan's offsets (no-op cost when the
+            # tensors already are views of one packed buffer with this layout)
+            hbuf = slot.buf.as_tensor(plan.staging_bytes)
+            for t, off, nb in zip(host_tensors, plan.offsets, plan.packed_nbytes):
+                if nb:
+                    src = t.contiguous().view(-1).view(torch.uint8)
+                    dst = hbuf[off : off + nb]
+                    if src.data_ptr() != dst.data_ptr():
+                        dst.copy_(src)
+            stream = self._current_stream()
+            if self._staging_free is not None:
+                stream_wait_event(stream, self._staging_free)
+            check(
+                self.lib.nvrx_fill(staging.ptr, slot.buf.data_ptr, plan.staging_bytes, self.drain_chunk, stream, None),
+                "nvrx_fill",
+            )
+            plan.scatter(staging.ptr, stream)
+            self.launches += 1 if plan.n_tiles else 0
+            done = Event(self.device)
+            done.record(stream)
+            self._staging_free = done
+            done.synchronize()  # the pinned slot is reused; restore is a blocking call like the reference's
+        finally:
+            self._release(slot)
+        return out
+
+    def restore_from_staging(self, plan: Plan, staging_ptr: int) -> None:
+        """Scatter a staging buffer that is already on the device (replica retrieval path)."""
+        plan.scatter(staging_ptr, self._current_stream())
+        self.launches += 1 if plan.n_tiles else 0
+
+    def close(self) -> None:
+        for plan in self._plans.values():
+            plan.close()
+        self._plans.clear()
+        for s in self._slots:
+            if s.done_event is not None:
+                try:
+                    s.done_event.synchronize()
+                except SnapError:
+                    pass
+            if s.buf is not None:
+                s.buf.close()
+                s.buf = None
+        if self._staging is not None:
+            self._staging.close()
+            self._staging = None
+
+
+def open_snapshot_views(desc: dict, timeout_ms: int = -1) -> Tuple[HostBuffer, List[torch.Tensor]]:
+    """Writer-process side: map the slot by name, wait (CPU only) for the drain, return tensor views."""
+    hb = HostBuffer.open(desc["shm_name"])
+    hb.wait(desc["progress_target"], timeout_ms)
+    layout: PackedLayout = desc["layout"]
+    return hb, layout.views(hb.as_tensor(layout.total_bytes))

@@ -1,0 +1,173 @@
+"""Packed replica exchange over NCCL / NVLink (the multi-GPU row of the hot path).
+
+Reference (``local/replication/group_utils.py:342-375`` ``all_gather_batch``): for every clique rank, for every
+tensor, one ``dist.broadcast`` into a fresh ``torch.empty_like`` followed by ``.to("cpu", non_blocking=True)`` --
+F x N NCCL launches and F x N D2H copies.  Here:
+
+    pack kernel  -> this rank's slice of the exchange buffer (HBM)
+    ONE all_gather_into_tensor over the clique (NVLink / NVSwitch)
+    ONE side-stream drain of the whole exchange buffer -> pinned host slot
+    result tensors = views of the slot, per source rank, in that rank's flattening order
+
+``send_packed`` / ``recv_packed`` are the point-to-point analogue used by the retrieve path
+(reference ``group_utils.py:378-449``): one packed ``dist.send`` / ``dist.recv`` + one scatter kernel.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from ._cabi import check
+from .engine import DEFAULT_ALIGN, DeviceBuffer, Event, PackedLayout, Snapshot, SnapshotEngine, dtype_name, expected_layout
+
+
+class _CudaBytes:
+    """``__cuda_array_interface__`` adaptor so c10d can address raw engine memory as a uint8 tensor."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,),
+            "typestr": "|u1",
+            "data": (ptr, False),
+            "version": 2,
+            "strides": None,
+        }
+
+
+def as_uint8_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
+    return torch.as_tensor(_CudaBytes(ptr, max(nbytes, 1)), device=torch.device("cuda", device))[:nbytes]
+
+
+def _exchange_buffer(engine: SnapshotEngine, nbytes: int) -> DeviceBuffer:
+    buf = getattr(engine, "_exchange_buf", None)
+    if buf is None or buf.nbytes < nbytes:
+        free_ev: Optional[Event] = getattr(engine, "_exchange_free", None)
+        if free_ev is not None:
+            free_ev.synchronize()
+        if buf is not None:
+            buf.close()
+        buf = DeviceBuffer(max(nbytes, 512), engine.device)
+        engine._exchange_buf = buf
+    return buf
+
+
+def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders, target_device):
+    """See module docstring.  ``all_placeholders[r]`` describes rank r's tensors (already all-gathered).
+
+    Returns ``(per-rank tensor lists, [Snapshot])``; with a CPU ``target_device`` the tensors are host views that
+    become valid once the snapshot has drained."""
+    my_tensors = [t.detach() if t.is_contiguous() else t.detach().contiguous() for t in my_tensors]
+    engine = SnapshotEngine.get(my_tensors[0].device.index)
+    world, me = group.world_size, group.my_group_rank
+    align = engine.align
+
+    layouts = []
+    for tps in all_placeholders:
+        offs, packed, total = expected_layout([tp.nbytes for tp in tps], [False] * len(tps), align)
+        layouts.append((offs, packed, total))
+    slot_bytes = max(total for _, _, total in layouts)
+    slot_bytes = (slot_bytes + 511) // 512 * 512
+
+    plan = engine._plan_for(my_tensors, [False] * len(my_tensors))
+    assert list(plan.offsets) == layouts[me][0] and plan.staging_bytes == layouts[me][2]
+
+    xbuf = _exchange_buffer(engine, world * slot_bytes)
+    stream = engine._current_stream()
+    free_ev = getattr(engine, "_exchange_free", None)
+    if free_ev is not None:
+        from .engine import stream_wait_event
+
+        stream_wait_event(stream, free_ev)  # previous drain of the exchange buffer must be over
+    plan.pack(xbuf.ptr + me * slot_bytes, stream)
+    engine.launches += 1 if plan.n_tiles else 0
+
+    whole = as_uint8_tensor(xbuf.ptr, world * slot_bytes, engine.device)
+    mine = whole[me * slot_bytes : (me + 1) * slot_bytes]
+    if world > 1:
+        dist.all_gather_into_tensor(whole, mine, group=group.group)
+
+    dev_lists = []
+    for r, (tps, (offs, packed, _)) in enumerate(zip(all_placeholders, layouts)):
+        lay = PackedLayout(
+            shapes=[tuple(tp.hollow_tensor.shape) for tp in tps],
+            dtypes=[dtype_name(tp.hollow_tensor.dtype) for tp in tps],
+            src_dtypes=[dtype_name(tp.hollow_tensor.dtype) for tp in tps],
+            offsets=[r * slot_bytes + o for o in offs],
+            packed_nbytes=list(packed),
+            total_bytes=world * slot_bytes,
+            align=align,
+        )
+        dev_lists.append(lay)
+
+    if target_device is None or torch.device(target_device).type == "cuda":
+        # stay on the device: hand out copies so the exchange buffer can be reused
+        result = [[v.clone() for v in lay.views(whole)] for lay in dev_lists]
+        return result, []
+
+    # land everything in ONE pinned host slot with one drain on the side stream
+    total = world * slot_bytes
+    slot = engine._acquire_slot(total)
+    packed_ev = Event(engine.device)
+    packed_ev.record(stream)
+    engine._side.wait_event(packed_ev)
+    base = slot.drained_total
+    check(
+        engine.lib.nvrx_drain(
+            slot.buf.data_ptr, xbuf.ptr, total, engine.drain_chunk, slot.buf.progress_ptr, base, engine._side.handle,
+            slot.done_event.handle,
+        ),
+        "nvrx_drain",
+    )
+    slot.drained_total = base + total
+    engine._exchange_free = slot.done_event
+
+    host = slot.buf.as_tensor(total)
+    result = [lay.views(host) for lay in dev_lists]
+    union = PackedLayout(
+        shapes=[s for lay in dev_lists for s in lay.shapes],
+        dtypes=[d for lay in dev_lists for d in lay.dtypes],
+        src_dtypes=[d for lay in dev_lists for d in lay.src_dtypes],
+        offsets=[o for lay in dev_lists for o in lay.offsets],
+        packed_nbytes=[n for lay in dev_lists for n in lay.packed_nbytes],
+        total_bytes=total,
+        align=align,
+    )
+    snap = Snapshot(engine=engine, slot=slot, layout=union, progress_target=slot.drained_total, n_total=len(union.shapes))
+    return result, [snap]
+
+
+def send_packed(group, tensors: Sequence[torch.Tensor], dst_global_rank: int) -> None:
+    """Pack ``tensors`` (CUDA, or CPU which are staged through the device first) and send ONE message."""
+    dev = torch.cuda.current_device()
+    engine = SnapshotEngine.get(dev)
+    cuda_tensors = [t if t.is_cuda else t.to(torch.device("cuda", dev)) for t in tensors]
+    cuda_tensors = [t.detach() if t.is_contiguous() else t.detach().contiguous() for t in cuda_tensors]
+    plan = engine._plan_for(cuda_tensors, [False] * len(cuda_tensors))
+    xbuf = _exchange_buffer(engine, plan.staging_bytes)
+    stream = engine._current_stream()
+    plan.pack(xbuf.ptr, stream)
+    engine.launches += 1 if plan.n_tiles else 0
+    dist.send(as_uint8_tensor(xbuf.ptr, plan.staging_bytes, dev), dst_global_rank, group=group.group)
+
+
+def recv_packed(group, dests: Sequence[torch.Tensor], src_global_rank: int) -> None:
+    """Receive ONE packed message and scatter it into ``dests`` (CUDA tensors, or CPU tensors filled through a
+    device bounce as the reference does at ``group_utils.py:442-446``)."""
+    dev = torch.cuda.current_device()
+    engine = SnapshotEngine.get(dev)
+    on_dev = [d if d.is_cuda else torch.empty(d.shape, dtype=d.dtype, device=torch.device("cuda", dev)) for d in dests]
+    assert all(d.is_contiguous() for d in on_dev)
+    plan = engine._plan_for(on_dev, [False] * len(on_dev))
+    xbuf = _exchange_buffer(engine, plan.staging_bytes)
+    dist.recv(as_uint8_tensor(xbuf.ptr, plan.staging_bytes, dev), src_global_rank, group=group.group)
+    stream = engine._current_stream()
+    plan.scatter(xbuf.ptr, stream)
+    engine.launches += 1 if plan.n_tiles else 0
+    for d, o in zip(dests, on_dev):
+        if not d.is_cuda:
+            d.copy_(o)
+    torch.cuda.current_stream(dev).synchronize()
