@@ -265,6 +265,19 @@ class HostBuffer:
         t._nvrx_hostbuf = self  # keep this object (not the mapping!) alive with the base tensor
         return t
 
+    def segment(self, offset: int, nbytes: int, dtype: torch.dtype, shape) -> torch.Tensor:
+        """Typed CPU tensor over ``[offset, offset + nbytes)`` of the payload with a *storage of its own*.
+
+        ``torch.save`` refuses tensors of different dtypes that share one storage, and would write the whole
+        slot for every view; one storage per segment gives the same file structure as the reference's
+        per-tensor host copies (one record per tensor) without copying anything."""
+        assert 0 <= offset and offset + nbytes <= self.capacity
+        if nbytes == 0:
+            return torch.empty(shape, dtype=dtype)
+        raw = (C.c_uint8 * nbytes).from_address(self.data_ptr + offset)
+        t = torch.frombuffer(raw, dtype=dtype).view(shape)
+        return t
+
     def write_fd(self, offset: int, nbytes: int, fd: int, file_off: int, threads: int = 8) -> None:
         check(self._lib.nvrx_hostbuf_write_fd(self._h, offset, nbytes, fd, file_off, threads), "nvrx_hostbuf_write_fd")
 
@@ -328,6 +341,14 @@ class PackedLayout:
         return out
 
 
+def host_views(layout: "PackedLayout", hb: "HostBuffer") -> List[torch.Tensor]:
+    """One CPU tensor per segment of ``layout`` inside host buffer ``hb`` (each with its own storage)."""
+    return [
+        hb.segment(off, nb, _DTYPE_NAMES[dt], shape)
+        for shape, dt, off, nb in zip(layout.shapes, layout.dtypes, layout.offsets, layout.packed_nbytes)
+    ]
+
+
 def expected_layout(nbytes: Sequence[int], narrow: Sequence[bool], align: int = DEFAULT_ALIGN) -> Tuple[List[int], List[int], int]:
     """Pure-Python statement of the layout rule in include/nvrx_snap.h (used for cross-checks only)."""
     offs, packed, cur = [], [], 0
@@ -378,7 +399,7 @@ class Snapshot:
 
         Their *content* is valid once :meth:`wait` returned / ``drained()`` is true -- same contract as the
         reference's ``tensor.to("cpu", non_blocking=True)`` before ``torch.cuda.synchronize()``."""
-        packed = self.layout.views(self.slot.buf.as_tensor(self.layout.total_bytes))
+        packed = host_views(self.layout, self.slot.buf)
         if not self.passthrough:
             return packed
         out, it = [], iter(packed)
@@ -669,4 +690,4 @@ def open_snapshot_views(desc: dict, timeout_ms: int = -1) -> Tuple[HostBuffer, L
     hb = HostBuffer.open(desc["shm_name"])
     hb.wait(desc["progress_target"], timeout_ms)
     layout: PackedLayout = desc["layout"]
-    return hb, layout.views(hb.as_tensor(layout.total_bytes))
+    return hb, host_views(layout, hb)

@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 from . import _cabi
 from ._cabi import check
-from .engine import DEFAULT_ALIGN, DeviceBuffer, Event, PackedLayout, Snapshot, SnapshotEngine, dtype_name, expected_layout
+from .engine import DeviceBuffer, Event, PackedLayout, Snapshot, SnapshotEngine, dtype_name, expected_layout, host_views
 
 
 class _CudaBytes:
@@ -125,8 +125,7 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
     slot.drained_total = base + total
     engine._exchange_free = slot.done_event
 
-    host = slot.buf.as_tensor(total)
-    result = [lay.views(host) for lay in dev_lists]
+    result = [host_views(lay, slot.buf) for lay in dev_lists]
     union = PackedLayout(
         shapes=[s for lay in dev_lists for s in lay.shapes],
         dtypes=[d for lay in dev_lists for d in lay.dtypes],

@@ -118,13 +118,16 @@ def _flatten_host(tensors: List[torch.Tensor], offs: List[int], total: int) -> t
 
 
 def _views_from_flat(flat: torch.Tensor, placeholders: List[TensorPlaceholder], offs: List[int]) -> List[torch.Tensor]:
+    """Typed tensors over slices of a flat host buffer, each with a storage of its own (``torch.save`` rejects
+    differently typed views of one storage)."""
+    raw = flat.numpy()
     out = []
     for tp, off in zip(placeholders, offs):
         meta = tp.hollow_tensor
         if tp.nbytes == 0:
-            out.append(torch.empty(meta.shape, dtype=meta.dtype, device=flat.device))
+            out.append(torch.empty(meta.shape, dtype=meta.dtype))
         else:
-            out.append(flat[off : off + tp.nbytes].view(meta.dtype).view(meta.shape))
+            out.append(torch.frombuffer(raw[off : off + tp.nbytes], dtype=meta.dtype).view(meta.shape))
     return out
 
 

@@ -18,8 +18,9 @@ PINNING (how this oracle is tied to the real reference; see tests/golden/make_go
                             -- golden JSON produced by calling the reference's own functions.
   * fp32->bf16 narrowing    -- DOES NOT EXIST in the reference ("parity unpinned" there); defined as
                                ``x.to(torch.bfloat16)`` and pinned against PyTorch (CPU for finite values and
-                               infinities; the NaN payload follows the CUDA ``cvt.rn.bf16.f32`` rule 0x7FFF,
-                               which PyTorch-CUDA produces and PyTorch-CPU (0x7FC0) does not).
+                               infinities; the NaN *payload* follows the CUDA ``cvt.rn.bf16.f32`` rule 0x7FFF,
+                               which is what PyTorch produces on CUDA tensors -- PyTorch-CPU is not even
+                               self-consistent there: 0xFFFF from its AVX-512 path, 0x7FC0 from the scalar one).
   * packed staging layout   -- new in this engine (the reference has no packed buffer); the restatement here
                                is the specification in include/nvrx_snap.h, checked against the C planner.
 """
@@ -93,7 +94,7 @@ def tensor_bytes(t: torch.Tensor) -> np.ndarray:
 # fp32 -> bf16 narrowing (new option; pinned against PyTorch, see header)
 # ----------------------------------------------------------------------------------------------------
 BF16_NAN_CUDA = 0x7FFF  # cvt.rn.bf16.f32 canonical NaN (what torch .to(bfloat16) yields on CUDA)
-BF16_NAN_TORCH_CPU = 0x7FC0  # c10::BFloat16 round_to_nearest_even on the host
+BF16_NAN_TORCH_CPU_SCALAR = 0x7FC0  # c10::BFloat16 round_to_nearest_even on the host (vectorised path: 0xFFFF)
 
 
 def f32_bits_to_bf16_bits(u32: np.ndarray, nan_bits: int = BF16_NAN_CUDA) -> np.ndarray:
