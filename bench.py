@@ -45,13 +45,14 @@ HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 # workload
 # ----------------------------------------------------------------------------------------------------
 def llama3_8b_shard_shapes():
-    """1/8 row shard of every Llama-3-8B tensor (vocab 128256, hidden 4096, 32 layers, ffn 14336, 32/8 heads)."""
+    """1/8 row shard (dim0 / 8) of every Llama-3-8B tensor (vocab 128256, hidden 4096, 32 layers, ffn 14336, 32/8
+    heads): 291 tensors, 1,003,782,656 parameters per rank."""
     shapes = [("embed", (16032, 4096))]
     for layer in range(32):
         for name, shp in (("q", (512, 4096)), ("k", (128, 4096)), ("v", (128, 4096)), ("o", (512, 4096)),
-                          ("gate", (1792, 4096)), ("up", (1792, 4096)), ("down", (512, 14336)), ("ln1", (4096,)), ("ln2", (4096,))):
+                          ("gate", (1792, 4096)), ("up", (1792, 4096)), ("down", (512, 14336)), ("ln1", (512,)), ("ln2", (512,))):
             shapes.append((f"layers.{layer}.{name}", shp))
-    shapes += [("final_ln", (4096,)), ("lm_head", (16032, 4096))]
+    shapes += [("final_ln", (512,)), ("lm_head", (16032, 4096))]
     return shapes
 
 

@@ -496,8 +496,11 @@ class SnapshotEngine:
             self._staging = DeviceBuffer(max(nbytes, 512), self.device)
         return self._staging
 
-    def _acquire_slot(self, nbytes: int) -> _Slot:
-        slot = next((s for s in self._slots if not s.busy), None)
+    def _acquire_slot(self, nbytes: int, slot: Optional[_Slot] = None) -> _Slot:
+        if slot is None:
+            # prefer a free slot that is already large enough (no re-pinning), then any free slot
+            free = [s for s in self._slots if not s.busy]
+            slot = next((s for s in free if s.buf is not None and s.buf.capacity >= nbytes), free[0] if free else None)
         if slot is None:
             raise SnapError(
                 _cabi.E_STATE,
@@ -528,7 +531,7 @@ class SnapshotEngine:
         self._ensure_staging(nbytes)
         for s in self._slots:
             if not s.busy:
-                self._acquire_slot(nbytes)
+                self._acquire_slot(nbytes, s)
                 self._release(s)
 
     # ---- planning -------------------------------------------------------------------------------

@@ -16,6 +16,19 @@ import torch
 DRAIN_TIMEOUT_MS = int(os.environ.get("NVRX_B200_DRAIN_TIMEOUT_MS", str(30 * 60 * 1000)))
 
 
+def fast_zip_writes() -> None:
+    """Writer-process setting: do not compute zip CRC32s in ``torch.save``.
+
+    ``torch.load`` never verifies them (checked with a zeroed CRC field, plain and ``mmap=True`` loads), but
+    computing them is the dominant cost of ``torch.save`` for multi-GB payloads (single-threaded crc32 over the
+    whole snapshot).  ``NVRX_B200_ZIP_CRC=1`` keeps them."""
+    if os.environ.get("NVRX_B200_ZIP_CRC", "0") in ("", "0"):
+        try:
+            torch.serialization.set_crc32_options(False)
+        except Exception:  # noqa: BLE001 - older PyTorch without the switch
+            pass
+
+
 def drain_aware(fn):
     """Mark ``fn`` as following the snapshot drain itself: async callers then skip the device-wide
     ``torch.cuda.synchronize()`` the reference needs before forking (``async_ckpt/core.py:345``)."""
@@ -71,6 +84,7 @@ def save_snapshot_with_torch(skeleton: Any, path, desc: Dict, *save_args, **save
     hb, views = open_snapshot_views(desc, DRAIN_TIMEOUT_MS)
     try:
         obj = _materialise(skeleton, views)
+        fast_zip_writes()
         torch.save(obj, path, *save_args, **save_kwargs)
     finally:
         del views

@@ -24,7 +24,7 @@ from typing import Any, Iterable, Optional, Tuple
 import torch
 
 from ...async_ckpt.core import AsyncRequest
-from ...b200.persist import wait_for_snapshots
+from ...b200.persist import fast_zip_writes, wait_for_snapshots
 from ...utils import _disable_gc, debug_time
 from ..base_state_dict import TensorAwareStateDict
 from ..replication.group_utils import GroupWrapper
@@ -109,6 +109,8 @@ class BaseCheckpointManager(ABC):
     @_disable_gc()
     def _save_fn(self, id_to_state_dict, snapshot_descs=()):
         held = wait_for_snapshots(snapshot_descs)  # CPU-only wait for the drain(s); no CUDA in the writer
+        if snapshot_descs:
+            fast_zip_writes()
         ckpt_id = None
         try:
             for ckpt_id, state_dict in id_to_state_dict.items():
