@@ -148,6 +148,18 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(label_prefix):
+    """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` capture."""
+    p = ROOT / "profiles" / "r01_ncu_walk_summary.json"
+    try:
+        for k in json.load(open(p))["kernels"]:
+            if k["label"].startswith(label_prefix):
+                return float(k["traffic_bytes"])
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def init_dist(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -246,7 +258,8 @@ def run_engine(args, rank, world, local):
         ok = len(lt) == len(tensors)
         for a, b in list(zip(lt, tensors))[:: max(1, len(tensors) // 64)]:
             want = b.to(torch.bfloat16).cpu() if (args.narrow and b.dtype == torch.float32 and b.numel() > 0) else b.cpu()
-            ok &= a.dtype == want.dtype and torch.equal(a.view(torch.uint8) if a.numel() else a, want.view(torch.uint8) if want.numel() else want)
+            ok &= a.dtype == want.dtype and a.shape == want.shape and (
+                a.numel() == 0 or torch.equal(a.contiguous().view(-1).view(torch.uint8), want.contiguous().view(-1).view(torch.uint8)))
         check = "bit-exact" if ok else "MISMATCH"
         del loaded, lt
     ckpt.close()
@@ -293,7 +306,8 @@ def run_engine(args, rank, world, local):
         "gpu_launches": launches,
         "roofline": {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": args.traffic_bytes, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+            "traffic": args.traffic_bytes or ncu_traffic("pack LDG narrow" if args.narrow else "pack TMA"),
+            "traffic_source": "profiles/r01_ncu_walk_summary.json (ncu --set full, same state, one launch)", "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
             "kernel": "nvrx::walk_tma<pack>" if not args.narrow else "nvrx::walk_ldg<pack> (narrow)",
         },
         "clocks": clocks.summary(),

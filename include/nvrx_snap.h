@@ -107,6 +107,12 @@ int nvrx_scatter(nvrx_plan* plan, const void* staging, void* stream);
 int nvrx_pack_sharded(nvrx_plan* plan, void* const* peer_bases, int n_peers, uint64_t shard_bytes,
                       uint64_t slot_offset, void* stream);
 
+/* Fused pack + all-gather (reference-identical full replication, strategies.py:88-140): every packed byte is
+ * written to ALL `n_peers` buffers at peer_bases[j] + slot_offset + position.  The source tensors are read from
+ * HBM once; remote copies travel as NVLink P2P stores issued by the same kernel (TMA bulk stores from the one
+ * shared-memory slot, or STG.128 on the ragged path).  Callers order it between two clique barriers. */
+int nvrx_pack_broadcast(nvrx_plan* plan, void* const* peer_bases, int n_peers, uint64_t slot_offset, void* stream);
+
 /* ---- drain: device staging -> pinned host on a side stream ------------------------------------
  * Replaces the device-wide torch.cuda.synchronize() stall of async_ckpt/torch_ckpt.py:50,
  * local/ckpt_managers/base_manager.py:306-309 and async_ckpt/core.py:345.

@@ -422,7 +422,32 @@ int nvrx_pack_sharded(nvrx_plan* p, void* const* peer_bases, int n_peers, uint64
     PeerMap pm;
     memset(&pm, 0, sizeof(pm));
     pm.n_peers = n_peers;
+    pm.mode = nvrx::kPeerShard;
     pm.shard_bytes = shard_bytes;
+    pm.slot_off = slot_offset;
+    for (int j = 0; j < n_peers; ++j) {
+        if (!peer_bases[j] || (reinterpret_cast<uintptr_t>(peer_bases[j]) & 511u)) return NVRX_E_INVALID;
+        pm.bases[j] = static_cast<uint8_t*>(peer_bases[j]);
+    }
+    return launch<nvrx::kDirPack>(p, nullptr, pm, st);
+}
+
+int nvrx_pack_broadcast(nvrx_plan* p, void* const* peer_bases, int n_peers, uint64_t slot_offset, void* stream) {
+    if (!p || !peer_bases || n_peers < 1 || n_peers > 16) return NVRX_E_INVALID;
+    if (slot_offset & 511u) return NVRX_E_INVALID;
+    DeviceGuard guard(p->device);
+    if (p->shard_bytes) {
+        p->shard_bytes = 0;
+        int rc = build_tiles(p);
+        if (rc) return rc;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = upload(p, st);
+    if (rc) return rc;
+    PeerMap pm;
+    memset(&pm, 0, sizeof(pm));
+    pm.n_peers = n_peers;
+    pm.mode = nvrx::kPeerBroadcast;
     pm.slot_off = slot_offset;
     for (int j = 0; j < n_peers; ++j) {
         if (!peer_bases[j] || (reinterpret_cast<uintptr_t>(peer_bases[j]) & 511u)) return NVRX_E_INVALID;

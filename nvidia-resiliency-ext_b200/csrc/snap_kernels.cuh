@@ -33,14 +33,20 @@ struct __align__(16) TileDesc {  // one per work granule (16 B)
     uint64_t off;     // tensor-side byte offset inside the segment
 };
 
-// Sharded destination for the fused pack+exchange: staging position p lives in
-// bases[p / shard_bytes] + slot_off + p % shard_bytes.  n_peers == 0 -> single local buffer.
+// Destinations of the fused pack+exchange.  Sharded: staging position p lives in
+// bases[p / shard_bytes] + slot_off + p % shard_bytes.
+// n_peers == 0 -> single local buffer.  mode kPeerShard: position p goes to ONE peer (all-to-all layout);
+// mode kPeerBroadcast: every byte is written to ALL bases at slot_off + p (pack fused with an all-gather:
+// the source is read from HBM once and stored over NVLink P2P to each clique member's exchange buffer).
 struct PeerMap {
     uint8_t* bases[16];
     uint64_t shard_bytes;
     uint64_t slot_off;
     int n_peers;
+    int mode;
 };
+constexpr int kPeerShard = 1;
+constexpr int kPeerBroadcast = 2;
 
 constexpr uint32_t kSegNarrow = 0x1u;
 constexpr int kDirPack = 0;
@@ -251,25 +257,30 @@ __device__ __forceinline__ void widen_bytes(uint8_t* __restrict__ dst, const uin
 }
 
 // staging address of packed position `pos`
-__device__ __forceinline__ uint8_t* stg_addr(uint8_t* staging, const PeerMap& pm, uint64_t pos) {
+__device__ __forceinline__ uint8_t* stg_addr(uint8_t* staging, const PeerMap& pm, uint64_t pos, int peer = 0) {
     if (pm.n_peers == 0) return staging + pos;
+    if (pm.mode == kPeerBroadcast) return pm.bases[peer] + pm.slot_off + pos;
     const uint64_t j = pos / pm.shard_bytes;
     return pm.bases[j] + pm.slot_off + (pos - j * pm.shard_bytes);
 }
+__device__ __forceinline__ int n_copies(const PeerMap& pm) { return (pm.n_peers && pm.mode == kPeerBroadcast) ? pm.n_peers : 1; }
 
 // one tile, executed by a thread group
 template <int DIR, int UNROLL>
 __device__ __forceinline__ void run_tile(const SegDesc& sd, const TileDesc& td, uint8_t* staging, const PeerMap& pm,
                                          uint32_t tid, uint32_t nthr) {
     uint8_t* ten = reinterpret_cast<uint8_t*>(sd.ptr) + td.off;
-    if (sd.flags & kSegNarrow) {
-        uint8_t* stg = stg_addr(staging, pm, sd.stg_off + (td.off >> 1));
-        if (DIR == kDirPack) narrow_bytes<UNROLL>(stg, ten, td.nbytes, tid, nthr);
-        else widen_bytes<UNROLL>(ten, stg, td.nbytes, tid, nthr);
-    } else {
-        uint8_t* stg = stg_addr(staging, pm, sd.stg_off + td.off);
-        if (DIR == kDirPack) copy_bytes<UNROLL>(stg, ten, td.nbytes, tid, nthr);
-        else copy_bytes<UNROLL>(ten, stg, td.nbytes, tid, nthr);
+    const int copies = (DIR == kDirPack) ? n_copies(pm) : 1;  // broadcast re-reads the tile from L2, HBM sees it once
+    for (int c = 0; c < copies; ++c) {
+        if (sd.flags & kSegNarrow) {
+            uint8_t* stg = stg_addr(staging, pm, sd.stg_off + (td.off >> 1), c);
+            if (DIR == kDirPack) narrow_bytes<UNROLL>(stg, ten, td.nbytes, tid, nthr);
+            else widen_bytes<UNROLL>(ten, stg, td.nbytes, tid, nthr);
+        } else {
+            uint8_t* stg = stg_addr(staging, pm, sd.stg_off + td.off, c);
+            if (DIR == kDirPack) copy_bytes<UNROLL>(stg, ten, td.nbytes, tid, nthr);
+            else copy_bytes<UNROLL>(ten, stg, td.nbytes, tid, nthr);
+        }
     }
 }
 
@@ -389,10 +400,15 @@ walk_tma(const SegDesc* __restrict__ segs, const TileDesc* __restrict__ tiles, u
             const TileDesc td = tiles[first + i * stride];
             const SegDesc sd = segs[td.seg];
             const uint32_t s = i % STAGES;
-            uint8_t* g = (DIR == kDirPack) ? stg_addr(staging, pm, sd.stg_off + td.off)
-                                           : reinterpret_cast<uint8_t*>(sd.ptr) + td.off;
             mbar_wait(smem_u32(&full[s]), (i / STAGES) & 1u);
-            bulk_s2g(g, ring_base + s * stage_bytes, td.nbytes);
+            if (DIR == kDirPack) {
+                // one smem slot feeds every destination (own buffer + NVLink peers); one bulk group per tile
+                const int copies = n_copies(pm);
+                for (int c = 0; c < copies; ++c)
+                    bulk_s2g(stg_addr(staging, pm, sd.stg_off + td.off, c), ring_base + s * stage_bytes, td.nbytes);
+            } else {
+                bulk_s2g(reinterpret_cast<uint8_t*>(sd.ptr) + td.off, ring_base + s * stage_bytes, td.nbytes);
+            }
             bulk_commit();
             if (i + LOADS < n_my) {
                 // slot (i+LOADS)%STAGES was last read by the store of tile i+LOADS-STAGES

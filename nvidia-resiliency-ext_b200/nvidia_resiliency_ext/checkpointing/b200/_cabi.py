@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "nvrx_pack",
     "nvrx_scatter",
     "nvrx_pack_sharded",
+    "nvrx_pack_broadcast",
     "nvrx_drain",
     "nvrx_fill",
     "nvrx_dev_alloc",
@@ -116,6 +117,7 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_pack": (_int, [_vp, _vp, _vp]),
         "nvrx_scatter": (_int, [_vp, _vp, _vp]),
         "nvrx_pack_sharded": (_int, [_vp, P(_vp), _int, _u64, _u64, _vp]),
+        "nvrx_pack_broadcast": (_int, [_vp, P(_vp), _int, _u64, _vp]),
         "nvrx_drain": (_int, [_vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
         "nvrx_fill": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
         "nvrx_dev_alloc": (_int, [_int, _u64, P(_vp)]),

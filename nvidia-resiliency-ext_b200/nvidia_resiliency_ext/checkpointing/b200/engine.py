@@ -122,6 +122,12 @@ class Plan:
             "nvrx_pack_sharded",
         )
 
+    def pack_broadcast(self, peer_bases: Sequence[int], slot_offset: int, stream: int) -> None:
+        check(
+            self._lib.nvrx_pack_broadcast(self._h, _ptr_array(peer_bases), len(peer_bases), slot_offset, stream),
+            "nvrx_pack_broadcast",
+        )
+
     def close(self) -> None:
         if self._h:
             self._lib.nvrx_plan_destroy(self._h)

@@ -15,6 +15,9 @@ F x N NCCL launches and F x N D2H copies.  Here:
 
 from __future__ import annotations
 
+import ctypes as C
+import os
+import socket
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -48,11 +51,77 @@ def _exchange_buffer(engine: SnapshotEngine, nbytes: int) -> DeviceBuffer:
         free_ev: Optional[Event] = getattr(engine, "_exchange_free", None)
         if free_ev is not None:
             free_ev.synchronize()
+        _drop_peer_maps(engine)
         if buf is not None:
             buf.close()
         buf = DeviceBuffer(max(nbytes, 512), engine.device)
         engine._exchange_buf = buf
     return buf
+
+
+# ---- NVLink peer mapping of the exchange buffers (fused pack + all-gather) ---------------------------
+def _drop_peer_maps(engine: SnapshotEngine) -> None:
+    for pm in getattr(engine, "_peer_maps", {}).values():
+        for ptr in pm["imported"]:
+            engine.lib.nvrx_ipc_close(engine.device, ptr)
+    engine._peer_maps = {}
+
+
+def _exchange_mode() -> str:
+    return os.environ.get("NVRX_B200_EXCHANGE", "auto").lower()  # auto | p2p | nccl
+
+
+def _peer_bases(engine: SnapshotEngine, group, xbuf: DeviceBuffer) -> Optional[List[int]]:
+    """Device addresses of every clique member's exchange buffer as seen from this GPU (own buffer included),
+    or None when the clique cannot use NVLink P2P (members on different hosts, no peer access, or disabled).
+    Collective over ``group`` the first time a given buffer generation is used."""
+    mode = _exchange_mode()
+    if mode == "nccl" or group.world_size == 1:
+        return None
+    maps = getattr(engine, "_peer_maps", None)
+    if maps is None:
+        maps = engine._peer_maps = {}
+    key = (id(group.group), xbuf.ptr, xbuf.nbytes)
+    if key in maps:
+        return maps[key]["bases"]
+    mine = {"host": socket.gethostname(), "boot": _boot_id(), "dev": engine.device, "handle": xbuf.ipc_handle(), "nbytes": xbuf.nbytes}
+    infos = group.all_gather_object(mine)
+    me = group.my_group_rank
+    ok = all(i["host"] == mine["host"] and i["boot"] == mine["boot"] and i["nbytes"] == xbuf.nbytes for i in infos)
+    ok = ok and all(r == me or torch.cuda.can_device_access_peer(engine.device, i["dev"]) for r, i in enumerate(infos))
+    votes = group.all_gather_object(bool(ok))
+    if not all(votes):
+        if mode == "p2p":
+            raise RuntimeError("NVRX_B200_EXCHANGE=p2p but the clique is not NVLink-peer reachable from every member")
+        maps[key] = {"bases": None, "imported": []}
+        return None
+    bases, imported = [], []
+    for r, info in enumerate(infos):
+        if r == me:
+            bases.append(xbuf.ptr)
+            continue
+        out = C.c_void_p()
+        check(engine.lib.nvrx_ipc_import(engine.device, info["handle"], C.byref(out)), "nvrx_ipc_import")
+        bases.append(out.value)
+        imported.append(out.value)
+    maps[key] = {"bases": bases, "imported": imported}
+    return bases
+
+
+def _boot_id() -> str:
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
+def _clique_barrier(engine: SnapshotEngine, group) -> None:
+    """Stream-ordered barrier over the clique (a 4-byte NCCL all-reduce): no CPU wait."""
+    tok = getattr(engine, "_barrier_token", None)
+    if tok is None:
+        tok = engine._barrier_token = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", engine.device))
+    dist.all_reduce(tok, group=group.group)
 
 
 def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders, target_device):
@@ -82,13 +151,24 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
         from .engine import stream_wait_event
 
         stream_wait_event(stream, free_ev)  # previous drain of the exchange buffer must be over
-    plan.pack(xbuf.ptr + me * slot_bytes, stream)
-    engine.launches += 1 if plan.n_tiles else 0
-
     whole = as_uint8_tensor(xbuf.ptr, world * slot_bytes, engine.device)
-    mine = whole[me * slot_bytes : (me + 1) * slot_bytes]
-    if world > 1:
-        dist.all_gather_into_tensor(whole, mine, group=group.group)
+    bases = _peer_bases(engine, group, xbuf)
+    if bases is not None:
+        # fused pack + all-gather: ONE kernel reads the tensors once and stores slice `me` into every member's
+        # exchange buffer (own HBM + NVLink P2P).  Barrier 1: every member's previous drain of its buffer is over;
+        # barrier 2: every member's stores have landed in mine.
+        _clique_barrier(engine, group)
+        plan.pack_broadcast(bases, me * slot_bytes, stream)
+        engine.launches += 1 if plan.n_tiles else 0
+        _clique_barrier(engine, group)
+        engine.last_exchange = "p2p-fused"
+    else:
+        plan.pack(xbuf.ptr + me * slot_bytes, stream)
+        engine.launches += 1 if plan.n_tiles else 0
+        mine = whole[me * slot_bytes : (me + 1) * slot_bytes]
+        if world > 1:
+            dist.all_gather_into_tensor(whole, mine, group=group.group)
+        engine.last_exchange = "nccl-allgather"
 
     dev_lists = []
     for r, (tps, (offs, packed, _)) in enumerate(zip(all_placeholders, layouts)):

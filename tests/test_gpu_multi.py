@@ -41,7 +41,10 @@ def flat_tensors(sd):
     return out
 
 
-def _w_allgather_batch(rank, world):
+def _w_allgather_batch(rank, world, mode):
+    import os
+
+    os.environ["NVRX_B200_EXCHANGE"] = mode
     from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
     from nvidia_resiliency_ext.checkpointing.local.replication.group_utils import GroupWrapper
 
@@ -50,6 +53,7 @@ def _w_allgather_batch(rank, world):
     launches0 = SnapshotEngine.get().launches
     got = gw.all_gather_batch(mine, target_device="cpu")
     assert SnapshotEngine.get().launches == launches0 + 1  # ONE pack kernel; the reference does world*N broadcasts
+    assert SnapshotEngine.get().last_exchange == ("nccl-allgather" if mode == "nccl" else "p2p-fused")
     for s in gw.last_snapshots:
         s.wait()
     assert len(got) == world
@@ -67,8 +71,10 @@ def _w_allgather_batch(rank, world):
             assert a.is_cuda and bit_equal(a, b)
 
 
-def test_all_gather_batch_packed_exchange(built_library):
-    run_ranks(_w_allgather_batch, min(torch.cuda.device_count(), 8), backend="nccl")
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_all_gather_batch_packed_exchange(built_library, mode):
+    """p2p: pack fused with the all-gather (NVLink peer stores from the pack kernel); nccl: pack + one NCCL all-gather."""
+    run_ranks(_w_allgather_batch, min(torch.cuda.device_count(), 8), mode, backend="nccl")
 
 
 def _w_replicated_save_and_restore(rank, world, root, jump, factor, kill):
@@ -94,7 +100,7 @@ def _w_replicated_save_and_restore(rank, world, root, jump, factor, kill):
     # every replica file holds the owner's bits
     for m in members:
         tasd = torch.load(mgr.local_ckpt_dir / f"iter_0000004_{m}_local.pt", weights_only=False)
-        assert all(bit_equal(a, b) for a, b in zip(tasd.tensors, flat_tensors(rank_state(m, "cpu") if False else rank_state(m))))
+        assert all(bit_equal(a, b) for a, b in zip(tasd.tensors, flat_tensors(rank_state(m))))
     dist.barrier()
     if rank in kill:
         for p in mgr.local_ckpt_dir.iterdir():

@@ -11,9 +11,18 @@ if [[ $WHAT == all || $WHAT == bench ]]; then
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
   timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 fi
+if [[ $WHAT == multi ]]; then
+  timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi.log 2>&1
+  tail -30 gpurun_out/pytest_multi.log
+fi
+if [[ $WHAT == ncu_list ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk_ -c 40 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 10 --warmup 3 --e2e-steps 2 --e2e-warmup 1 --no-cpu-baseline --no-verify > gpurun_out/bench_under_ncu.log 2>&1
+  grep -c walk_ gpurun_out/launches.csv
+fi
 if [[ $WHAT == all || $WHAT == ncu ]]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 3 --warmup 3 --e2e-steps 1 --e2e-warmup 0 --no-cpu-baseline --no-verify > gpurun_out/bench_under_ncu.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk_ -c 40 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 10 --warmup 3 --e2e-steps 2 --e2e-warmup 1 --no-cpu-baseline --no-verify > gpurun_out/bench_under_ncu.log 2>&1
   grep -c walk_ gpurun_out/launches.csv
   NCU_REPS=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:walk_ -c 6 -f -o gpurun_out/prof_walk \
       python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1
