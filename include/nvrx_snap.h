@@ -173,6 +173,11 @@ int nvrx_hostbuf_wait(nvrx_hostbuf* hb, uint64_t value, int64_t timeout_ms);
  * pickle+write of local/ckpt_managers/local_manager.py:117-122 for the payload part). */
 int nvrx_hostbuf_write_fd(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int fd, uint64_t file_off,
                           int threads);
+/* Vectored form: n extents (payload offset, length, file offset) written by one pool of `threads` pwrite() workers.
+ * This is how a drained snapshot is persisted: torch.save lays out the container with its data records skipped
+ * (torch.serialization.skip_data) and the extents fill them in in parallel. */
+int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, const uint64_t* nbytes,
+                           const uint64_t* file_offs, int fd, int threads);
 /* crc32 (zlib polynomial) of a payload range computed with `threads` workers and combined. */
 int nvrx_hostbuf_crc32(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int threads, uint32_t* out);
 

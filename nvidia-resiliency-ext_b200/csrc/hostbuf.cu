@@ -269,21 +269,31 @@ int nvrx_hostbuf_wait(nvrx_hostbuf* hb, uint64_t value, int64_t timeout_ms) {
     }
 }
 
-int nvrx_hostbuf_write_fd(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int fd, uint64_t file_off, int threads) {
-    if (!hb || fd < 0 || offset > hb->capacity || bytes > hb->capacity - offset) return NVRX_E_INVALID;
-    if (bytes == 0) return NVRX_OK;
+int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, const uint64_t* nbytes, const uint64_t* file_offs,
+                           int fd, int threads) {
+    if (!hb || fd < 0 || n < 0 || (n > 0 && (!offsets || !nbytes || !file_offs))) return NVRX_E_INVALID;
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets[i] > hb->capacity || nbytes[i] > hb->capacity - offsets[i]) return NVRX_E_INVALID;
     if (threads < 1) threads = 1;
-    const uint8_t* base = hb->map + kHeaderBytes + offset;
+    const uint8_t* base = hb->map + kHeaderBytes;
     const uint64_t grain = 8ull << 20;
+    // work items: (extent, piece) pairs handed out through one atomic cursor over the piece prefix sums
+    std::vector<uint64_t> first_piece(static_cast<size_t>(n) + 1, 0);
+    for (int64_t i = 0; i < n; ++i) first_piece[i + 1] = first_piece[i] + (nbytes[i] + grain - 1) / grain;
+    const uint64_t total_pieces = first_piece[n];
+    if (total_pieces == 0) return NVRX_OK;
     std::atomic<uint64_t> next{0};
     std::atomic<int> err{0};
     auto worker = [&] {
-        while (!err.load()) {
-            const uint64_t o = next.fetch_add(grain);
-            if (o >= bytes) break;
-            uint64_t len = std::min<uint64_t>(grain, bytes - o), done = 0;
+        int64_t ext = 0;
+        while (!err.load(std::memory_order_relaxed)) {
+            const uint64_t piece = next.fetch_add(1);
+            if (piece >= total_pieces) break;
+            while (first_piece[ext + 1] <= piece) ++ext;  // pieces are handed out in increasing order per thread
+            const uint64_t o = (piece - first_piece[ext]) * grain;
+            uint64_t len = std::min<uint64_t>(grain, nbytes[ext] - o), done = 0;
             while (done < len) {
-                ssize_t w = pwrite(fd, base + o + done, len - done, static_cast<off_t>(file_off + o + done));
+                ssize_t w = pwrite(fd, base + offsets[ext] + o + done, len - done, static_cast<off_t>(file_offs[ext] + o + done));
                 if (w < 0) {
                     if (errno == EINTR) continue;
                     err.store(errno ? errno : EIO);
@@ -293,8 +303,9 @@ int nvrx_hostbuf_write_fd(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int
             }
         }
     };
+    const int nthreads = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(threads), total_pieces));
     std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
     worker();
     for (auto& th : pool) th.join();
     if (err.load()) {
@@ -302,6 +313,10 @@ int nvrx_hostbuf_write_fd(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int
         return NVRX_E_SYS;
     }
     return NVRX_OK;
+}
+
+int nvrx_hostbuf_write_fd(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int fd, uint64_t file_off, int threads) {
+    return nvrx_hostbuf_writev_fd(hb, 1, &offset, &bytes, &file_off, fd, threads);
 }
 
 int nvrx_hostbuf_crc32(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int threads, uint32_t* out) {

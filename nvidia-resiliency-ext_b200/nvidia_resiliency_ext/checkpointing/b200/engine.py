@@ -287,6 +287,13 @@ class HostBuffer:
     def write_fd(self, offset: int, nbytes: int, fd: int, file_off: int, threads: int = 8) -> None:
         check(self._lib.nvrx_hostbuf_write_fd(self._h, offset, nbytes, fd, file_off, threads), "nvrx_hostbuf_write_fd")
 
+    def writev_fd(self, offsets: Sequence[int], nbytes: Sequence[int], file_offs: Sequence[int], fd: int, threads: int = 8) -> None:
+        n = len(offsets)
+        check(
+            self._lib.nvrx_hostbuf_writev_fd(self._h, n, _u64_array(offsets), _u64_array(nbytes), _u64_array(file_offs), fd, threads),
+            "nvrx_hostbuf_writev_fd",
+        )
+
     def crc32(self, offset: int, nbytes: int, threads: int = 8) -> int:
         out = C.c_uint32()
         check(self._lib.nvrx_hostbuf_crc32(self._h, offset, nbytes, threads, C.byref(out)), "nvrx_hostbuf_crc32")
@@ -423,6 +430,8 @@ class Snapshot:
             "shm_name": self.slot.buf.name,
             "progress_target": self.progress_target,
             "layout": self.layout,
+            "owner_pid": os.getpid(),
+            "owner_base": self.slot.buf.data_ptr,  # where the trainer's views of the slot live (valid in fork children)
         }
 
     def release(self) -> None:

@@ -1,0 +1,121 @@
+"""``torch.save`` whose tensor payload is written by a pool of ``pwrite`` workers straight from snapshot slots.
+
+Stock ``torch.save`` pushes every storage through one thread (memcpy into the zip stream + crc32).  Here the
+container is produced by PyTorch itself with its data records *skipped* (``torch.serialization.skip_data``, a
+sparse file that already has every header, ``data.pkl`` and the central directory), and the records are then
+filled in place from the pinned shared-memory slot by ``nvrx_hostbuf_writev_fd``.  The result is an ordinary
+checkpoint file: ``torch.load`` (plain or ``mmap=True``) reads it, and it is record-for-record what
+``torch.save`` of the same object would have laid out.
+
+Replaces the payload part of the reference's single-threaded writer
+(``local/ckpt_managers/local_manager.py:117-122``, ``async_ckpt/torch_ckpt.py:36-41``).  CPU only; never calls CUDA.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pickle
+from contextlib import contextmanager
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+WRITE_THREADS = int(os.environ.get("NVRX_B200_WRITE_THREADS", "16"))
+
+# (base address, capacity, HostBuffer) ranges the current writer may find tensor storages in
+_active_ranges: List[Tuple[int, int, object]] = []
+
+
+@contextmanager
+def slot_ranges(ranges: Sequence[Tuple[int, int, object]]):
+    """Declare the snapshot slots tensors may live in while saving (used by the managers' writer functions)."""
+    ranges = list(ranges)
+    _active_ranges.extend(ranges)
+    try:
+        yield
+    finally:
+        if ranges:
+            del _active_ranges[-len(ranges) :]
+
+
+def ranges_for(descs, held) -> List[Tuple[int, int, object]]:
+    """Address ranges for the snapshot descriptors ``descs`` whose slots are mapped as ``held`` in this process.
+    A forked writer also sees the trainer's mapping (tensor views were created there) at the trainer's address."""
+    out = []
+    for desc, hb in zip(descs, held):
+        out.append((hb.data_ptr, hb.capacity, hb))
+        base = desc.get("owner_base")
+        if base and base != hb.data_ptr and desc.get("owner_pid") in (os.getppid(), os.getpid()):
+            out.append((base, hb.capacity, hb))
+    return out
+
+
+class _RecordingZip:
+    """Stands in for PyTorchFileWriter during a dry run of the pickler: remembers which storage became which
+    ``data/<key>`` record (by address), copies nothing."""
+
+    def __init__(self):
+        self.records: List[Tuple[str, int, int]] = []
+
+    def write_record(self, name, data, nbytes):
+        if name.startswith("data/") and not isinstance(data, (str, bytes)):
+            self.records.append((name, data.data_ptr(), int(nbytes)))
+
+    def write_record_metadata(self, name, nbytes):  # pragma: no cover - not used in the dry run
+        self.records.append((name, 0, int(nbytes)))
+
+
+def _locate(ptr: int, nbytes: int):
+    for base, cap, hb in _active_ranges:
+        if base <= ptr and ptr + nbytes <= base + cap:
+            return hb, ptr - base
+    return None, 0
+
+
+def save(obj, f, *args, **kwargs) -> str:
+    """Drop-in for ``torch.save(obj, f, ...)``.  Returns which path was taken: "parallel" or "torch"."""
+    if not _active_ranges or args or set(kwargs) - {"pickle_protocol"} or not hasattr(torch.serialization, "skip_data"):
+        torch.save(obj, f, *args, **kwargs)
+        return "torch"
+    protocol = kwargs.get("pickle_protocol", torch.serialization.DEFAULT_PROTOCOL)
+    try:
+        dry = _RecordingZip()
+        torch.serialization._save(obj, dry, pickle, protocol, False)
+        records = dry.records
+    except Exception:  # noqa: BLE001 - private API moved: use the stock writer
+        torch.save(obj, f, **kwargs)
+        return "torch"
+
+    is_path = isinstance(f, (str, os.PathLike))
+    start = 0 if is_path else f.tell()
+    with torch.serialization.skip_data():
+        torch.save(obj, f, **kwargs)
+    if not is_path:
+        f.flush()
+    name = os.fspath(f) if is_path else getattr(f, "name", None)
+    if start != 0 or not isinstance(name, (str, bytes)):
+        raise RuntimeError("fastsave.save needs a path or a file object opened on a named file at offset 0")
+    reader = torch._C.PyTorchFileReader(os.fspath(name))
+    fd = os.open(name, os.O_WRONLY) if is_path else f.fileno()
+    try:
+        by_slot = {}
+        for rec, ptr, nbytes in records:
+            if nbytes == 0:
+                continue
+            file_off = reader.get_record_offset(rec)
+            hb, off = _locate(ptr, nbytes)
+            if hb is None:  # a tensor that does not live in a snapshot slot (pass-through host tensor)
+                os.pwrite(fd, C.string_at(ptr, nbytes), file_off)
+                continue
+            ent = by_slot.setdefault(id(hb), (hb, [], [], []))
+            ent[1].append(off)
+            ent[2].append(nbytes)
+            ent[3].append(file_off)
+        for hb, offs, sizes, file_offs in by_slot.values():
+            hb.writev_fd(offs, sizes, file_offs, fd, WRITE_THREADS)
+    finally:
+        del reader
+        if is_path:
+            os.close(fd)
+    return "parallel"

@@ -79,13 +79,15 @@ def save_snapshot_with_torch(skeleton: Any, path, desc: Dict, *save_args, **save
     are views of ONE storage (the slot), so the file holds a single storage record written sequentially and
     ``torch.load`` returns tensors that compare equal to the reference's own ``torch.save`` of the CPU copies.
     """
+    from . import fastsave
     from .engine import open_snapshot_views
 
     hb, views = open_snapshot_views(desc, DRAIN_TIMEOUT_MS)
     try:
         obj = _materialise(skeleton, views)
         fast_zip_writes()
-        torch.save(obj, path, *save_args, **save_kwargs)
+        with fastsave.slot_ranges(fastsave.ranges_for([desc], [hb])):
+            fastsave.save(obj, path, *save_args, **save_kwargs)
     finally:
         del views
         hb.close(unlink=False)

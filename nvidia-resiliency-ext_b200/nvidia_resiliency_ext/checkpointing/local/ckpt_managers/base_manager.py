@@ -24,6 +24,7 @@ from typing import Any, Iterable, Optional, Tuple
 import torch
 
 from ...async_ckpt.core import AsyncRequest
+from ...b200 import fastsave
 from ...b200.persist import fast_zip_writes, wait_for_snapshots
 from ...utils import _disable_gc, debug_time
 from ..base_state_dict import TensorAwareStateDict
@@ -113,12 +114,14 @@ class BaseCheckpointManager(ABC):
             fast_zip_writes()
         ckpt_id = None
         try:
-            for ckpt_id, state_dict in id_to_state_dict.items():
-                try:
-                    self._save(state_dict, ckpt_id)
-                except Exception as exc:
-                    logging.error(f"Exception caught during saving {ckpt_id}: {exc}", exc_info=True)
-                    raise
+            # backends that save through b200.fastsave.save() get the payload written in parallel from the slots
+            with fastsave.slot_ranges(fastsave.ranges_for(snapshot_descs, held)):
+                for ckpt_id, state_dict in id_to_state_dict.items():
+                    try:
+                        self._save(state_dict, ckpt_id)
+                    except Exception as exc:
+                        logging.error(f"Exception caught during saving {ckpt_id}: {exc}", exc_info=True)
+                        raise
         finally:
             for hb in held:
                 hb.close(unlink=False)

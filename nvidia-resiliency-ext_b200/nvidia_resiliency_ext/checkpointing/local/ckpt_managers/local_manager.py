@@ -14,6 +14,7 @@ from typing import Iterable, Optional, Tuple, Union
 
 import torch
 
+from ...b200 import fastsave
 from ...utils import debug_time
 from ..base_state_dict import TensorAwareStateDict
 from ..replication.strategies import ReplicationStrategy
@@ -103,7 +104,7 @@ class LocalCheckpointManager(BaseCheckpointManager):
         try:
             logging.info(f"Saving to {str(dirty)}")
             with open(dirty, "bx") as fh:  # exclusive create: a second writer on this machine must fail
-                torch.save(state_dict, fh)  # nosec B614
+                fastsave.save(state_dict, fh)  # torch.save format; payload by parallel pwrite when it sits in a slot  # nosec B614
             final = self._local_ckpt_path_from_id(ckpt_id, False)
             logging.info(f"Renaming {str(dirty)} to {final}")
             dirty.rename(target=final)

@@ -1,0 +1,116 @@
+"""Host snapshot buffers and the parallel checkpoint writer, CPU only (no CUDA calls: pin=False)."""
+import os
+import threading
+import time
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+
+def make_hb(nbytes, name=None):
+    from nvidia_resiliency_ext.checkpointing.b200.engine import HostBuffer
+
+    return HostBuffer.create(nbytes, name=name, pin=False, prefault_threads=2)
+
+
+def test_hostbuf_create_open_wait_crc(built_library):
+    from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
+    from nvidia_resiliency_ext.checkpointing.b200.engine import HostBuffer
+
+    name = f"/nvrx_test_{os.getpid()}"
+    hb = make_hb(3_000_000, name)
+    assert hb.capacity >= 3_000_000 and hb.data_ptr % 4096 == 0 and hb.progress == 0
+    buf = hb.as_tensor(3_000_000)
+    rng = np.random.default_rng(0)
+    payload = rng.integers(0, 256, 3_000_000, dtype=np.uint8)
+    buf.numpy()[:] = payload
+    # crc32 in parallel pieces + combine == zlib
+    for off, n, thr in ((0, 3_000_000, 1), (0, 3_000_000, 7), (13, 2_999_000, 3), (5, 0, 4), (100, 17, 16)):
+        assert hb.crc32(off, n, thr) == zlib.crc32(payload[off : off + n].tobytes())
+    # a second mapping (what a writer process does) sees the same bytes and the progress word
+    other = HostBuffer.open(name)
+    assert other.capacity == hb.capacity
+    assert np.array_equal(other.as_tensor(1000).numpy(), payload[:1000])
+    with pytest.raises(SnapError):
+        other.wait(1, timeout_ms=50)  # nothing drained yet -> timeout
+    import ctypes as C
+
+    def drain_later():
+        time.sleep(0.1)
+        C.c_uint64.from_address(hb.progress_ptr).value = 42
+
+    t = threading.Thread(target=drain_later)
+    t.start()
+    other.wait(42, timeout_ms=5000)
+    t.join()
+    assert other.progress == 42
+    other.close()
+    with pytest.raises(SnapError):
+        HostBuffer.open("/nvrx_test_does_not_exist")
+    hb.close()
+    with pytest.raises(SnapError):
+        HostBuffer.open(name)  # unlinked by the owner
+
+
+def test_segment_views_have_own_storage_and_save(built_library, tmp_path):
+    hb = make_hb(1 << 20)
+    a = hb.segment(0, 4000, torch.float32, (10, 100))
+    b = hb.segment(4096, 800, torch.int64, (100,))
+    a.copy_(torch.arange(1000, dtype=torch.float32).view(10, 100))
+    b.copy_(torch.arange(100))
+    assert a.untyped_storage().nbytes() == 4000 and b.untyped_storage().nbytes() == 800
+    torch.save({"a": a, "b": b}, tmp_path / "x.pt")  # differently typed views of ONE storage would be refused
+    x = torch.load(tmp_path / "x.pt")
+    assert torch.equal(x["a"], a) and torch.equal(x["b"], b)
+    del a, b
+    hb.close()
+
+
+@pytest.mark.parametrize("as_file_object", [False, True])
+def test_parallel_writer_produces_a_plain_torch_checkpoint(built_library, tmp_path, as_file_object):
+    from nvidia_resiliency_ext.checkpointing.b200 import fastsave
+
+    hb = make_hb(64 << 20)
+    g = torch.Generator().manual_seed(0)
+    specs = [((1000, 1000), torch.float32), ((3,), torch.int64), ((0, 5), torch.float32), ((), torch.float32), ((4097,), torch.bfloat16),
+             ((2048, 2048), torch.float32), ((77,), torch.uint8)]
+    views, off = [], 0
+    for shape, dt in specs:
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        off = (off + 511) // 512 * 512
+        v = hb.segment(off, n, dt, shape)
+        if v.numel():
+            src = torch.randn(shape, generator=g) * 100 if dt.is_floating_point else torch.randint(0, 200, shape, generator=g)
+            v.copy_(src.to(dt))
+        views.append(v)
+        off += n
+    foreign = torch.arange(10.0)  # a tensor that does not live in the slot
+    obj = {"slot": views, "nested": {"f": foreign, "txt": "hello", "again": views[0]}, "n": 3}
+    path = tmp_path / "fast.pt"
+    with fastsave.slot_ranges([(hb.data_ptr, hb.capacity, hb)]):
+        if as_file_object:
+            with open(path, "bx") as fh:
+                how = fastsave.save(obj, fh)
+        else:
+            how = fastsave.save(obj, path)
+    assert how == "parallel"
+    torch.save(obj, tmp_path / "stock.pt")
+    fast, stock = torch.load(path), torch.load(tmp_path / "stock.pt")
+    for a, b in zip(fast["slot"], stock["slot"]):
+        assert a.dtype == b.dtype and a.shape == b.shape and (a.numel() == 0 or torch.equal(a.view(-1).view(torch.uint8), b.view(-1).view(torch.uint8)))
+    assert torch.equal(fast["nested"]["f"], foreign) and fast["nested"]["txt"] == "hello" and fast["n"] == 3
+    assert fast["nested"]["again"].data_ptr() == fast["slot"][0].data_ptr()  # shared storage preserved, as with stock torch.save
+    # same container layout as stock torch.save: same records at the same offsets
+    r1, r2 = torch._C.PyTorchFileReader(str(path)), torch._C.PyTorchFileReader(str(tmp_path / "stock.pt"))
+    recs = sorted(r1.get_all_records())
+    assert recs == sorted(r2.get_all_records())
+    if not as_file_object:  # (a file object is archived under the generic name "archive": different header lengths)
+        assert all(r1.get_record_offset(n) - r2.get_record_offset(n) == r1.get_record_offset("data/0") - r2.get_record_offset("data/0")
+                   for n in recs if n.startswith("data/"))
+    assert torch.equal(torch.load(path, mmap=True)["slot"][5], stock["slot"][5])
+    # outside a slot context the stock writer is used
+    assert fastsave.save(obj, tmp_path / "plain.pt") == "torch"
+    del views, obj, fast, stock
+    hb.close()
