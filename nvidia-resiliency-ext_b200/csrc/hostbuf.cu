@@ -1,8 +1,11 @@
 // hostbuf.cu -- host snapshot buffers of the C ABI: one POSIX shared-memory mapping per snapshot slot,
 // page-locked for DMA, followed by CPU-only processes through a progress word in its header page.
 #include <cuda_runtime.h>
+#include <ctype.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <sched.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,7 +37,43 @@ struct Header {
 };
 static_assert(sizeof(Header) == 128, "header layout");
 
-void prefault(uint8_t* base, uint64_t bytes, int threads) {
+// CPUs of the NUMA node the GPU hangs off (empty set if sysfs does not say): the slot is first-touched from
+// those CPUs so its pages land in the DRAM next to the GPU's PCIe root port and the drain does not cross sockets.
+bool numa_cpus_of_device(int device, cpu_set_t* set) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) return false;
+    for (char* c = bdf; *c; ++c) *c = static_cast<char>(tolower(*c));
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return false;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        const int n = sscanf(tok, "%d-%d", &lo, &hi);
+        if (n == 1) hi = lo;
+        if (n < 1) continue;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) {
+            CPU_SET(c, set);
+            ++count;
+        }
+    }
+    return count > 0;
+}
+
+void prefault(uint8_t* base, uint64_t bytes, int threads, const cpu_set_t* cpus) {
     if (threads < 1) threads = 1;
     const uint64_t page = 4096;
     const uint64_t per = ((bytes / threads) + page - 1) / page * page;
@@ -43,6 +82,7 @@ void prefault(uint8_t* base, uint64_t bytes, int threads) {
         const uint64_t lo = std::min<uint64_t>(bytes, per * t), hi = std::min<uint64_t>(bytes, per * (t + 1));
         if (lo >= hi) break;
         pool.emplace_back([=] {
+            if (cpus) sched_setaffinity(0, sizeof(cpu_set_t), cpus);  // this thread only; it exits after touching
             for (uint64_t o = lo; o < hi; o += page) base[o] = 0;
         });
     }
@@ -175,7 +215,11 @@ int nvrx_hostbuf_create(const char* shm_name, uint64_t bytes, int prefault_threa
     hb->owner = true;
     hb->device = device;
     if (shm_name) hb->name = shm_name;
-    if (prefault_threads > 0) prefault(hb->map, total, prefault_threads);
+    if (prefault_threads > 0) {
+        cpu_set_t cpus;
+        const bool local = pin && !getenv("NVRX_B200_NO_NUMA") && numa_cpus_of_device(device, &cpus);
+        prefault(hb->map, total, prefault_threads, local ? &cpus : nullptr);
+    }
     Header* h = reinterpret_cast<Header*>(hb->map);
     h->magic = kMagic;
     h->capacity = hb->capacity;
