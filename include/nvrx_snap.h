@@ -122,6 +122,13 @@ int nvrx_pack_broadcast(nvrx_plan* plan, void* const* peer_bases, int n_peers, u
  * memory can follow the drain without touching CUDA.  If `done_event` != NULL it is recorded at the end. */
 int nvrx_drain(void* host_dst, const void* staging, uint64_t bytes, uint64_t chunk_bytes,
                volatile uint64_t* progress, uint64_t base_value, void* stream, void* done_event);
+/* Pipelined pack + drain, the whole snapshot in one call: the packed range is cut into `chunk_bytes` chunks; chunk c is
+ * packed by its own sub-launch on `pack_stream` (tiles in staging order) and copied to `host_dst` on `drain_stream` as
+ * soon as that sub-launch has finished, so the D2H starts ~100 us after the call instead of after the full pack.
+ * `progress`/`base_value` as in nvrx_drain.  `packed_event` (optional) is recorded on pack_stream after the last
+ * sub-launch -- the training stream is free from there; `done_event` (optional) on drain_stream after the last copy. */
+int nvrx_snapshot(nvrx_plan* plan, void* staging, void* host_dst, uint64_t chunk_bytes, volatile uint64_t* progress,
+                  uint64_t base_value, void* pack_stream, void* drain_stream, void* packed_event, void* done_event);
 /* Mirror for restore: pinned host -> device staging (H2D), optional event. */
 int nvrx_fill(void* staging, const void* host_src, uint64_t bytes, uint64_t chunk_bytes, void* stream,
               void* done_event);

@@ -15,6 +15,7 @@
 using nvrx::PeerMap;
 using nvrx::SegDesc;
 using nvrx::TileDesc;
+using nvrx::TileSpan;
 
 #define NVRX_CUDA(expr)                                   \
     do {                                                  \
@@ -72,6 +73,7 @@ struct nvrx_plan {
     size_t tiles_cap = 0;  // capacity (entries) of h_tiles / d_tiles
     uint32_t n_bulk = 0, n_tiles = 0;
     bool segs_dirty = true, tiles_dirty = true;
+    std::vector<cudaEvent_t> chunk_events;  // pack -> drain hand-off of the pipelined snapshot
 };
 
 namespace {
@@ -182,41 +184,71 @@ int pick_stages(uint32_t tile_bytes) {
 }
 
 template <int DIR, int STAGES, int LOADS>
-int launch_tma(nvrx_plan* p, uint8_t* staging, const PeerMap& pm, cudaStream_t st) {
+int launch_tma(nvrx_plan* p, const TileSpan& span, uint8_t* staging, const PeerMap& pm, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(STAGES) * p->tile_bytes;
     auto kern = nvrx::walk_tma<DIR, STAGES, LOADS>;
     NVRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     uint32_t per_sm = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 2048))));
     if (const char* env = getenv("NVRX_B200_TMA_CTAS_PER_SM")) per_sm = std::max(1, atoi(env));
     uint32_t grid = static_cast<uint32_t>(p->sm_count) * per_sm;
-    const uint32_t need = std::max<uint32_t>(p->n_bulk, (p->n_tiles - p->n_bulk + 2) / 3);
+    const uint32_t need = std::max<uint32_t>(span.na, (span.nb + 2) / 3);
     grid = std::max<uint32_t>(1, std::min(grid, need));
-    kern<<<grid, nvrx::kTmaThreads, smem, st>>>(p->d_segs, p->d_tiles, p->n_bulk, p->n_tiles, staging, p->tile_bytes, pm);
+    kern<<<grid, nvrx::kTmaThreads, smem, st>>>(p->d_segs, span, staging, p->tile_bytes, pm);
     NVRX_CUDA(cudaGetLastError());
     return NVRX_OK;
 }
 
 template <int DIR>
-int launch(nvrx_plan* p, uint8_t* staging, const PeerMap& pm, cudaStream_t st) {
-    if (p->n_tiles == 0) return NVRX_OK;
+int launch_span(nvrx_plan* p, const TileSpan& span, uint8_t* staging, const PeerMap& pm, cudaStream_t st) {
+    if (span.na + span.nb == 0) return NVRX_OK;
     int variant = p->variant;
     if (variant == NVRX_VARIANT_AUTO) variant = (p->any_narrow || p->n_bulk == 0) ? NVRX_VARIANT_LDG : NVRX_VARIANT_TMA;
     if (variant == NVRX_VARIANT_TMA) {
         switch (pick_stages(p->tile_bytes)) {
-            case 12: return launch_tma<DIR, 12, 8>(p, staging, pm, st);
-            case 8: return launch_tma<DIR, 8, 6>(p, staging, pm, st);
-            case 6: return launch_tma<DIR, 6, 4>(p, staging, pm, st);
-            case 4: return launch_tma<DIR, 4, 3>(p, staging, pm, st);
-            default: return launch_tma<DIR, 3, 2>(p, staging, pm, st);
+            case 12: return launch_tma<DIR, 12, 8>(p, span, staging, pm, st);
+            case 8: return launch_tma<DIR, 8, 6>(p, span, staging, pm, st);
+            case 6: return launch_tma<DIR, 6, 4>(p, span, staging, pm, st);
+            case 4: return launch_tma<DIR, 4, 3>(p, span, staging, pm, st);
+            default: return launch_tma<DIR, 3, 2>(p, span, staging, pm, st);
         }
     }
     uint32_t per_sm = 4;
     if (const char* env = getenv("NVRX_B200_LDG_CTAS_PER_SM")) per_sm = std::max(1, atoi(env));
     uint32_t grid = static_cast<uint32_t>(p->sm_count) * per_sm;
-    grid = std::max<uint32_t>(1, std::min(grid, p->n_tiles));
-    nvrx::walk_ldg<DIR><<<grid, nvrx::kLdgThreads, 0, st>>>(p->d_segs, p->d_tiles, p->n_tiles, staging, pm);
+    grid = std::max<uint32_t>(1, std::min(grid, span.na + span.nb));
+    nvrx::walk_ldg<DIR><<<grid, nvrx::kLdgThreads, 0, st>>>(p->d_segs, span, staging, pm);
     NVRX_CUDA(cudaGetLastError());
     return NVRX_OK;
+}
+
+TileSpan whole_span(const nvrx_plan* p) {
+    TileSpan s;
+    s.a = p->d_tiles;
+    s.na = p->n_bulk;
+    s.b = p->d_tiles + p->n_bulk;
+    s.nb = p->n_tiles - p->n_bulk;
+    return s;
+}
+
+template <int DIR>
+int launch(nvrx_plan* p, uint8_t* staging, const PeerMap& pm, cudaStream_t st) {
+    return launch_span<DIR>(p, whole_span(p), staging, pm, st);
+}
+
+// staging position of a tile (bulk and ragged lists are each sorted by it: tiles are emitted in segment order)
+inline uint64_t tile_pos(const nvrx_plan* p, const TileDesc& t) {
+    const bool narrow = (p->flags[t.seg] & NVRX_SEG_NARROW_F32_BF16) != 0;
+    return p->off[t.seg] + (narrow ? t.off / 2 : t.off);
+}
+
+// first index in tiles[lo, hi) whose staging position is >= pos
+uint32_t lower_tile(const nvrx_plan* p, uint32_t lo, uint32_t hi, uint64_t pos) {
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (tile_pos(p, p->h_tiles[mid]) < pos) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
 }
 
 }  // namespace
@@ -322,6 +354,7 @@ int nvrx_plan_destroy(nvrx_plan* p) {
     if (p->h_tiles) cudaFreeHost(p->h_tiles);
     if (p->d_segs) cudaFree(p->d_segs);
     if (p->d_tiles) cudaFree(p->d_tiles);
+    for (cudaEvent_t ev : p->chunk_events) cudaEventDestroy(ev);
     delete p;
     return NVRX_OK;
 }
@@ -430,6 +463,71 @@ int nvrx_pack_sharded(nvrx_plan* p, void* const* peer_bases, int n_peers, uint64
         pm.bases[j] = static_cast<uint8_t*>(peer_bases[j]);
     }
     return launch<nvrx::kDirPack>(p, nullptr, pm, st);
+}
+
+int nvrx_snapshot(nvrx_plan* p, void* staging, void* host_dst, uint64_t chunk_bytes, volatile uint64_t* progress,
+                  uint64_t base_value, void* pack_stream, void* drain_stream, void* packed_event, void* done_event) {
+    if (!p || (p->staging_bytes && (!staging || !host_dst))) return NVRX_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(staging) & 511u) return NVRX_E_INVALID;
+    DeviceGuard guard(p->device);
+    if (p->shard_bytes) {
+        p->shard_bytes = 0;
+        int rc = build_tiles(p);
+        if (rc) return rc;
+    }
+    cudaStream_t ps = static_cast<cudaStream_t>(pack_stream), ds = static_cast<cudaStream_t>(drain_stream);
+    int rc = upload(p, ps);
+    if (rc) return rc;
+    const uint64_t total = p->staging_bytes;
+    if (chunk_bytes == 0 || chunk_bytes > total) chunk_bytes = total ? total : 1;
+    chunk_bytes = round_up(chunk_bytes, 512);
+    uint64_t n_chunks = total ? (total + chunk_bytes - 1) / chunk_bytes : 0;
+    if (n_chunks > 256) {  // keep the number of launches bounded
+        chunk_bytes = round_up((total + 255) / 256, 512);
+        n_chunks = (total + chunk_bytes - 1) / chunk_bytes;
+    }
+    while (p->chunk_events.size() < n_chunks) {
+        cudaEvent_t ev;
+        NVRX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        p->chunk_events.push_back(ev);
+    }
+    void* prog_dev = nullptr;
+    if (progress) NVRX_CUDA(cudaHostGetDevicePointer(&prog_dev, const_cast<uint64_t*>(progress), 0));
+    PeerMap pm;
+    memset(&pm, 0, sizeof(pm));
+    uint32_t b_lo = 0, r_lo = p->n_bulk;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const uint64_t end_pos = std::min(total, (c + 1) * chunk_bytes);
+        // chunk c = every tile that STARTS before end_pos and was not launched yet; a tile reaching into chunk c+1
+        // is complete before chunk c+1's event, which is what that chunk's copy waits for
+        const uint32_t b_hi = (c + 1 == n_chunks) ? p->n_bulk : lower_tile(p, b_lo, p->n_bulk, end_pos);
+        const uint32_t r_hi = (c + 1 == n_chunks) ? p->n_tiles : lower_tile(p, r_lo, p->n_tiles, end_pos);
+        TileSpan span;
+        span.a = p->d_tiles + b_lo;
+        span.na = b_hi - b_lo;
+        span.b = p->d_tiles + r_lo;
+        span.nb = r_hi - r_lo;
+        rc = launch_span<nvrx::kDirPack>(p, span, static_cast<uint8_t*>(staging), pm, ps);
+        if (rc) return rc;
+        b_lo = b_hi;
+        r_lo = r_hi;
+        NVRX_CUDA(cudaEventRecord(p->chunk_events[c], ps));
+        NVRX_CUDA(cudaStreamWaitEvent(ds, p->chunk_events[c], 0));
+        const uint64_t begin = c * chunk_bytes;
+        NVRX_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(host_dst) + begin, static_cast<const uint8_t*>(staging) + begin,
+                                  end_pos - begin, cudaMemcpyDeviceToHost, ds));
+        if (prog_dev) {
+            rc = nvrx_stream_write_u64(ds, prog_dev, base_value + end_pos);
+            if (rc) return rc;
+        }
+    }
+    if (n_chunks == 0 && prog_dev) {
+        rc = nvrx_stream_write_u64(ds, prog_dev, base_value);
+        if (rc) return rc;
+    }
+    if (packed_event) NVRX_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(packed_event), ps));
+    if (done_event) NVRX_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(done_event), ds));
+    return NVRX_OK;
 }
 
 int nvrx_pack_broadcast(nvrx_plan* p, void* const* peer_bases, int n_peers, uint64_t slot_offset, void* stream) {

@@ -67,6 +67,14 @@ __device__ __forceinline__ void st_stream(int4* p, const int4& v) {
                  "r"(v.z), "r"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ int2 ld_stream64(const int2* p) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream64(int2* p, const int2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -172,42 +180,40 @@ __device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint
 }
 
 // fp32 -> bf16 narrowing copy: n = source bytes (multiple of 4), dst receives n/2 bytes.
+// Lane-contiguous on both sides: each thread turns ONE 16-byte vector (4 floats) into ONE 8-byte vector, so a warp
+// reads 512 contiguous bytes and writes 256 contiguous bytes per instruction (every 32-byte sector fully used; the
+// 2 x LDG.128 -> 1 x STG.128 per-thread shape strides lanes by 32 B and touches every sector twice).
 template <int UNROLL>
 __device__ __forceinline__ void narrow_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n,
                                              uint32_t tid, uint32_t nthr) {
     const uint32_t nelem = n >> 2;
     uint32_t done = 0;  // elements handled by the vector body
-    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
-        const uint32_t nvec = nelem >> 3;  // 8 floats (2 x int4) -> 8 bf16 (1 x int4)
+    if (((reinterpret_cast<uintptr_t>(src) & 15u) | (reinterpret_cast<uintptr_t>(dst) & 7u)) == 0) {
+        const uint32_t nvec = nelem >> 2;  // 4 floats (int4) -> 4 bf16 (int2)
         const int4* s4 = reinterpret_cast<const int4*>(src);
-        int4* d4 = reinterpret_cast<int4*>(dst);
+        int2* d2 = reinterpret_cast<int2*>(dst);
+        constexpr int U = 2 * UNROLL;
         uint32_t i = tid;
-        for (; i + (UNROLL - 1) * nthr < nvec; i += UNROLL * nthr) {
-            int4 lo[UNROLL], hi[UNROLL];
+        for (; i + (U - 1) * nthr < nvec; i += U * nthr) {
+            int4 v[U];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                lo[u] = ld_stream(s4 + 2 * (i + u * nthr));
-                hi[u] = ld_stream(s4 + 2 * (i + u * nthr) + 1);
-            }
+            for (int u = 0; u < U; ++u) v[u] = ld_stream(s4 + i + u * nthr);
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                int4 o;
-                o.x = cvt_bf16x2(lo[u].x, lo[u].y);
-                o.y = cvt_bf16x2(lo[u].z, lo[u].w);
-                o.z = cvt_bf16x2(hi[u].x, hi[u].y);
-                o.w = cvt_bf16x2(hi[u].z, hi[u].w);
-                st_stream(d4 + i + u * nthr, o);
+            for (int u = 0; u < U; ++u) {
+                int2 o;
+                o.x = cvt_bf16x2(v[u].x, v[u].y);
+                o.y = cvt_bf16x2(v[u].z, v[u].w);
+                st_stream64(d2 + i + u * nthr, o);
             }
         }
         for (; i < nvec; i += nthr) {
-            int4 lo = ld_stream(s4 + 2 * i), hi = ld_stream(s4 + 2 * i + 1), o;
-            o.x = cvt_bf16x2(lo.x, lo.y);
-            o.y = cvt_bf16x2(lo.z, lo.w);
-            o.z = cvt_bf16x2(hi.x, hi.y);
-            o.w = cvt_bf16x2(hi.z, hi.w);
-            st_stream(d4 + i, o);
+            const int4 v = ld_stream(s4 + i);
+            int2 o;
+            o.x = cvt_bf16x2(v.x, v.y);
+            o.y = cvt_bf16x2(v.z, v.w);
+            st_stream64(d2 + i, o);
         }
-        done = nvec << 3;
+        done = nvec << 2;
     }
     const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
     uint16_t* d16 = reinterpret_cast<uint16_t*>(dst);
@@ -215,41 +221,42 @@ __device__ __forceinline__ void narrow_bytes(uint8_t* __restrict__ dst, const ui
 }
 
 // bf16 -> fp32 widening copy (exact): n = destination bytes (multiple of 4), src holds n/2 bytes.
+// Mirror shape: ONE 8-byte load (4 bf16) -> ONE 16-byte store per thread, lane-contiguous on both sides.
 template <int UNROLL>
 __device__ __forceinline__ void widen_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n,
                                             uint32_t tid, uint32_t nthr) {
     const uint32_t nelem = n >> 2;
     uint32_t done = 0;
-    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
-        const uint32_t nvec = nelem >> 3;
-        const int4* s4 = reinterpret_cast<const int4*>(src);
+    if (((reinterpret_cast<uintptr_t>(src) & 7u) | (reinterpret_cast<uintptr_t>(dst) & 15u)) == 0) {
+        const uint32_t nvec = nelem >> 2;
+        const int2* s2 = reinterpret_cast<const int2*>(src);
         int4* d4 = reinterpret_cast<int4*>(dst);
+        constexpr int U = 2 * UNROLL;
         uint32_t i = tid;
-        for (; i + (UNROLL - 1) * nthr < nvec; i += UNROLL * nthr) {
-            int4 v[UNROLL];
+        for (; i + (U - 1) * nthr < nvec; i += U * nthr) {
+            int2 v[U];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(s4 + i + u * nthr);
+            for (int u = 0; u < U; ++u) v[u] = ld_stream64(s2 + i + u * nthr);
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                int4 lo, hi;
-                lo.x = v[u].x << 16; lo.y = v[u].x & 0xffff0000u;
-                lo.z = v[u].y << 16; lo.w = v[u].y & 0xffff0000u;
-                hi.x = v[u].z << 16; hi.y = v[u].z & 0xffff0000u;
-                hi.z = v[u].w << 16; hi.w = v[u].w & 0xffff0000u;
-                st_stream(d4 + 2 * (i + u * nthr), lo);
-                st_stream(d4 + 2 * (i + u * nthr) + 1, hi);
+            for (int u = 0; u < U; ++u) {
+                int4 o;
+                o.x = v[u].x << 16;
+                o.y = v[u].x & 0xffff0000u;
+                o.z = v[u].y << 16;
+                o.w = v[u].y & 0xffff0000u;
+                st_stream(d4 + i + u * nthr, o);
             }
         }
         for (; i < nvec; i += nthr) {
-            int4 v = ld_stream(s4 + i), lo, hi;
-            lo.x = v.x << 16; lo.y = v.x & 0xffff0000u;
-            lo.z = v.y << 16; lo.w = v.y & 0xffff0000u;
-            hi.x = v.z << 16; hi.y = v.z & 0xffff0000u;
-            hi.z = v.w << 16; hi.w = v.w & 0xffff0000u;
-            st_stream(d4 + 2 * i, lo);
-            st_stream(d4 + 2 * i + 1, hi);
+            const int2 v = ld_stream64(s2 + i);
+            int4 o;
+            o.x = v.x << 16;
+            o.y = v.x & 0xffff0000u;
+            o.z = v.y << 16;
+            o.w = v.y & 0xffff0000u;
+            st_stream(d4 + i, o);
         }
-        done = nvec << 3;
+        done = nvec << 2;
     }
     const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
     uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
@@ -291,13 +298,22 @@ __device__ __forceinline__ void run_tile(const SegDesc& sd, const TileDesc& td, 
 constexpr int kLdgThreads = 256;
 constexpr int kLdgUnroll = 4;
 
+// A launch covers two index ranges of the tile table (the bulk and the ragged tiles of one staging chunk).
+struct TileSpan {
+    const TileDesc* a;
+    const TileDesc* b;
+    uint32_t na, nb;
+    __device__ __forceinline__ TileDesc at(uint32_t t) const { return t < na ? a[t] : b[t - na]; }
+    __device__ __forceinline__ uint32_t size() const { return na + nb; }
+};
+
 template <int DIR>
 __global__ void __launch_bounds__(kLdgThreads, 4)
-walk_ldg(const SegDesc* __restrict__ segs, const TileDesc* __restrict__ tiles, uint32_t ntiles, uint8_t* staging,
-         const __grid_constant__ PeerMap pm) {
+walk_ldg(const SegDesc* __restrict__ segs, const TileSpan span, uint8_t* staging, const __grid_constant__ PeerMap pm) {
+    const uint32_t ntiles = span.size();
     uint32_t t = blockIdx.x;
     if (t >= ntiles) return;
-    TileDesc td = tiles[t];
+    TileDesc td = span.at(t);
     SegDesc sd = segs[td.seg];
     while (true) {
         const uint32_t tn = t + gridDim.x;
@@ -305,7 +321,7 @@ walk_ldg(const SegDesc* __restrict__ segs, const TileDesc* __restrict__ tiles, u
         SegDesc sd_n;
         const bool more = tn < ntiles;
         if (more) {
-            td_n = tiles[tn];
+            td_n = span.at(tn);
             sd_n = segs[td_n.seg];
         }
         run_tile<DIR, kLdgUnroll>(sd, td, staging, pm, threadIdx.x, kLdgThreads);
@@ -318,8 +334,8 @@ walk_ldg(const SegDesc* __restrict__ segs, const TileDesc* __restrict__ tiles, u
 
 // ------------------------------------------------------------------------------------------------
 // walker 2: TMA bulk-copy ring + ragged warps.
-//   tiles[0, nbulk)        : both sides 16-B aligned, nbytes % 16 == 0, nbytes <= stage_bytes, bit copy
-//   tiles[nbulk, ntiles)   : everything else
+//   span.a[0, na) : bulk tiles -- both sides 16-B aligned, nbytes % 16 == 0, nbytes <= stage_bytes, bit copy
+//   span.b[0, nb) : ragged tiles -- everything else
 // ------------------------------------------------------------------------------------------------
 constexpr int kTmaThreads = 128;
 
@@ -362,8 +378,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // smem->global stores may still be reading their slot.
 template <int DIR, int STAGES, int LOADS>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-walk_tma(const SegDesc* __restrict__ segs, const TileDesc* __restrict__ tiles, uint32_t nbulk, uint32_t ntiles,
-         uint8_t* staging, uint32_t stage_bytes, const __grid_constant__ PeerMap pm) {
+walk_tma(const SegDesc* __restrict__ segs, const TileSpan span, uint8_t* staging, uint32_t stage_bytes,
+         const __grid_constant__ PeerMap pm) {
+    const TileDesc* __restrict__ tiles = span.a;
+    const uint32_t nbulk = span.na;
     static_assert(LOADS >= 1 && LOADS < STAGES, "need at least one slot for stores in flight");
     extern __shared__ __align__(1024) uint8_t ring[];
     __shared__ __align__(8) uint64_t full[STAGES];
@@ -421,10 +439,10 @@ walk_tma(const SegDesc* __restrict__ segs, const TileDesc* __restrict__ tiles, u
     }
 
     // ---- ragged warps: one warp per tile ----
-    const uint32_t nrag = ntiles - nbulk;
+    const uint32_t nrag = span.nb;
     const uint32_t nw = (kTmaThreads / 32) - 1;
     for (uint32_t r = blockIdx.x * nw + (warp - 1); r < nrag; r += gridDim.x * nw) {
-        const TileDesc td = tiles[nbulk + r];
+        const TileDesc td = span.b[r];
         const SegDesc sd = segs[td.seg];
         run_tile<DIR, 4>(sd, td, staging, pm, lane, 32);
     }

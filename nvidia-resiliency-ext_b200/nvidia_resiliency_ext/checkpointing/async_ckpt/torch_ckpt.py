@@ -41,13 +41,17 @@ class TorchAsyncCheckpoint(object):
             request = AsyncRequest(TorchAsyncCheckpoint.async_fn, (preload_tensors(state_dict), *args), [], kwargs or {})
             self._async_calls_queue.schedule_async_request(request)
             return
-        _, snap = preload_tensors(state_dict, narrow=self._narrow, return_snapshot=True)
+        devices = {t.device.index for t in tensors if t.is_cuda}
+        if len(devices) != 1 or not all(t.is_cuda for t in tensors):
+            raise ValueError("async_save: all tensors of the state dict must live on one CUDA device (or all on the host)")
+        from ..b200.engine import SnapshotEngine
+
+        # GPU work first (pack sub-launches + drain are enqueued here), Python bookkeeping while it runs
+        snap = SnapshotEngine.get(devices.pop()).snapshot(tensors, narrow=self._narrow)
         counter = iter(range(len(tensors)))
         skeleton = dict_list_map_outplace(
             lambda v: SnapshotRef(next(counter)) if isinstance(v, torch.Tensor) else v, state_dict
         )
-        if snap.passthrough:
-            raise ValueError("async_save: mixing CUDA and CPU tensors in one state dict is not supported")
         path, rest = args[0], args[1:]
         request = AsyncRequest(save_snapshot_with_torch, (skeleton, path, snap.descriptor(), *rest), [], kwargs or {})
         idx = self._async_calls_queue.schedule_async_request(request)

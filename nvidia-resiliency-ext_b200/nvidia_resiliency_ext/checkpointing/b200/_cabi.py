@@ -44,6 +44,7 @@ EXPORTED_SYMBOLS = (
     "nvrx_pack_sharded",
     "nvrx_pack_broadcast",
     "nvrx_drain",
+    "nvrx_snapshot",
     "nvrx_fill",
     "nvrx_dev_alloc",
     "nvrx_dev_free",
@@ -120,6 +121,7 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_pack_sharded": (_int, [_vp, P(_vp), _int, _u64, _u64, _vp]),
         "nvrx_pack_broadcast": (_int, [_vp, P(_vp), _int, _u64, _vp]),
         "nvrx_drain": (_int, [_vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
+        "nvrx_snapshot": (_int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]),
         "nvrx_fill": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
         "nvrx_dev_alloc": (_int, [_int, _u64, P(_vp)]),
         "nvrx_dev_free": (_int, [_int, _vp]),

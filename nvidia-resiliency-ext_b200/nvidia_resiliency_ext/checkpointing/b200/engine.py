@@ -33,7 +33,7 @@ from . import _cabi
 from ._cabi import SnapError, check
 
 DEFAULT_ALIGN = 512
-DEFAULT_DRAIN_CHUNK = 256 << 20
+DEFAULT_DRAIN_CHUNK = int(os.environ.get("NVRX_B200_DRAIN_CHUNK_MB", "256")) << 20
 
 
 def _ptr_array(values: Sequence[int]):
@@ -577,9 +577,10 @@ class SnapshotEngine:
         Returns as soon as the pack kernel and the side-stream copy are *enqueued*."""
         all_tensors = list(tensors)
         passthrough = {i: t for i, t in enumerate(all_tensors) if not (t.is_cuda and t.device.index == self.device)}
-        cuda_tensors = [t.detach() for i, t in enumerate(all_tensors) if i not in passthrough]
+        cuda_tensors = [t for i, t in enumerate(all_tensors) if i not in passthrough] if passthrough else all_tensors
         # the kernel walks contiguous byte ranges; strided tensors are compacted first (rare)
-        cuda_tensors = [t if t.is_contiguous() else t.contiguous() for t in cuda_tensors]
+        if not all(t.is_contiguous() for t in cuda_tensors):
+            cuda_tensors = [t if t.is_contiguous() else t.detach().contiguous() for t in cuda_tensors]
         mask = self._narrow_mask(cuda_tensors, narrow)
         plan = self._plan_for(cuda_tensors, mask)
 
@@ -591,24 +592,32 @@ class SnapshotEngine:
             stream_wait_event(stream, self._staging_free)
 
         start = stop = None
+        base = slot.drained_total
         if self.timing:
+            # separate launches so the pack kernel can be timed on its own (bench / profiling)
             start, stop = Event(self.device, timing=True), Event(self.device, timing=True)
             plan.commit(stream)
             start.record(stream)
-        plan.pack(staging.ptr, stream)
-        self.launches += 1 if plan.n_tiles else 0
-        packed = stop if stop is not None else Event(self.device)
-        packed.record(stream)
-
-        self._side.wait_event(packed)
-        base = slot.drained_total
-        check(
-            self.lib.nvrx_drain(
-                slot.buf.data_ptr, staging.ptr, plan.staging_bytes, self.drain_chunk, slot.buf.progress_ptr, base,
-                self._side.handle, slot.done_event.handle,
-            ),
-            "nvrx_drain",
-        )
+            plan.pack(staging.ptr, stream)
+            stop.record(stream)
+            self._side.wait_event(stop)
+            check(
+                self.lib.nvrx_drain(
+                    slot.buf.data_ptr, staging.ptr, plan.staging_bytes, self.drain_chunk, slot.buf.progress_ptr, base,
+                    self._side.handle, slot.done_event.handle,
+                ),
+                "nvrx_drain",
+            )
+        else:
+            # pipelined: chunk c is copied out as soon as its sub-launch of the pack kernel has finished
+            check(
+                self.lib.nvrx_snapshot(
+                    plan._h, staging.ptr, slot.buf.data_ptr, self.drain_chunk, slot.buf.progress_ptr, base, stream,
+                    self._side.handle, None, slot.done_event.handle,
+                ),
+                "nvrx_snapshot",
+            )
+        self.launches += (-(-plan.staging_bytes // self.drain_chunk) if not self.timing else 1) if plan.n_tiles else 0
         slot.drained_total = base + plan.staging_bytes
         self._staging_free = slot.done_event
 

@@ -293,6 +293,15 @@ class GroupWrapper:
         hollow, placeholders = self.recv_object(src)
         hollow.init_tensors()
         dests = list(hollow.tensors)
+        if self._payload_on_gpu():
+            # the skeleton remembers the *sender's* device index; when sender and receiver use different local GPUs
+            # (cliques inside one node) the payload must land on this rank's device, not the sender's
+            here = torch.device("cuda", torch.cuda.current_device())
+            moved = [torch.empty_like(d, device=here) if d.is_cuda and d.device != here else d for d in dests]
+            if any(m is not d for m, d in zip(moved, dests)):
+                hollow.pop_tensors()
+                hollow.insert_tensors(moved)
+                dests = moved
         nbytes = sum(t.nbytes for t in dests)
         if nbytes:
             if self._payload_on_gpu():

@@ -29,7 +29,7 @@ def _entry(rank, world, port, backend, fn, args, errq):
         raise
 
 
-def run_ranks(fn, world: int, *args, backend: str = "gloo", timeout: float = 300.0):
+def run_ranks(fn, world: int, *args, backend: str = "gloo", timeout: float = 150.0):
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
     port = free_port()
