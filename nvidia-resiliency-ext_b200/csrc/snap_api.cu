@@ -212,7 +212,7 @@ int launch_span(nvrx_plan* p, const TileSpan& span, uint8_t* staging, const Peer
             default: return launch_tma<DIR, 3, 2>(p, span, staging, pm, st);
         }
     }
-    uint32_t per_sm = 4;
+    uint32_t per_sm = 8;  // measured: 8 CTAs/SM worth of grid beats 4 (profiles/r01_selftest_sweep2.log)
     if (const char* env = getenv("NVRX_B200_LDG_CTAS_PER_SM")) per_sm = std::max(1, atoi(env));
     uint32_t grid = static_cast<uint32_t>(p->sm_count) * per_sm;
     grid = std::max<uint32_t>(1, std::min(grid, span.na + span.nb));

@@ -114,3 +114,44 @@ def test_parallel_writer_produces_a_plain_torch_checkpoint(built_library, tmp_pa
     assert fastsave.save(obj, tmp_path / "plain.pt") == "torch"
     del views, obj, fast, stock
     hb.close()
+
+
+def _fake_snapshot(name):
+    """A drained snapshot slot built by hand (no GPU): two tensors + descriptor as SnapshotEngine would produce."""
+    import ctypes as C
+
+    from nvidia_resiliency_ext.checkpointing.b200.engine import PackedLayout
+
+    hb = make_hb(1 << 20, name)
+    a = torch.arange(1000, dtype=torch.float32).view(10, 100)
+    b = torch.arange(77, dtype=torch.int64)
+    layout = PackedLayout(shapes=[(10, 100), (77,)], dtypes=["float32", "int64"], src_dtypes=["float32", "int64"], offsets=[0, 4096],
+                          packed_nbytes=[4000, 616], total_bytes=4096 + 1024)
+    hb.segment(0, 4000, torch.float32, (10, 100)).copy_(a)
+    hb.segment(4096, 616, torch.int64, (77,)).copy_(b)
+    C.c_uint64.from_address(hb.progress_ptr).value = layout.total_bytes  # "drain finished"
+    desc = {"shm_name": name, "progress_target": layout.total_bytes, "layout": layout, "owner_pid": os.getpid(), "owner_base": hb.data_ptr}
+    return hb, desc, a, b
+
+
+def test_writer_side_of_a_snapshot_in_process_and_spawned(built_library, tmp_path):
+    """What the persistent worker runs for TorchAsyncCheckpoint.async_save: map the slot by name, wait for the
+    drain, persist -- here against a hand-made slot so it runs without a GPU."""
+    import torch.multiprocessing as mp
+
+    from nvidia_resiliency_ext.checkpointing.b200.persist import SnapshotRef, save_snapshot_with_torch
+
+    name = f"/nvrx_test_w_{os.getpid()}"
+    hb, desc, a, b = _fake_snapshot(name)
+    skeleton = {"model": {"a": SnapshotRef(0)}, "opt": [SnapshotRef(1), "x"], "it": 9}
+    save_snapshot_with_torch(skeleton, tmp_path / "inproc.pt", desc)
+    got = torch.load(tmp_path / "inproc.pt")
+    assert torch.equal(got["model"]["a"], a) and torch.equal(got["opt"][0], b) and got["opt"][1] == "x" and got["it"] == 9
+    ctx = mp.get_context("spawn")
+    p = ctx.Process(target=save_snapshot_with_torch, args=(skeleton, str(tmp_path / "spawned.pt"), desc))
+    p.start()
+    p.join(120)
+    assert p.exitcode == 0
+    got = torch.load(tmp_path / "spawned.pt")
+    assert torch.equal(got["model"]["a"], a) and torch.equal(got["opt"][0], b)
+    hb.close()

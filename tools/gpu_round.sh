@@ -15,6 +15,20 @@ if [[ $WHAT == multi ]]; then
   timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi.log 2>&1
   tail -30 gpurun_out/pytest_multi.log
 fi
+if [[ $WHAT == repl ]]; then
+  NG=${2:-2}; SCALE=${3:-1.0}
+  for MODE in p2p nccl; do
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2961$NG \
+        tools/bench_replicate.py --scale $SCALE --mode $MODE --iters 3 > gpurun_out/repl_${NG}_${MODE}.json 2> gpurun_out/repl_${NG}_${MODE}.err
+    tail -2 gpurun_out/repl_${NG}_${MODE}.err; cat gpurun_out/repl_${NG}_${MODE}.json
+  done
+fi
+if [[ $WHAT == scale ]]; then
+  NG=${2:-2}
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2962$NG \
+      bench.py --gpus $NG > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err
+  tail -2 gpurun_out/bench_n$NG.err; cat gpurun_out/bench_n$NG.json
+fi
 if [[ $WHAT == ncu_list ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk_ -c 40 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 10 --warmup 3 --e2e-steps 2 --e2e-warmup 1 --no-cpu-baseline --no-verify > gpurun_out/bench_under_ncu.log 2>&1
