@@ -99,12 +99,12 @@ int nvrx_plan_commit(nvrx_plan* plan, void* stream);
 int nvrx_pack(nvrx_plan* plan, void* staging, void* stream);
 int nvrx_scatter(nvrx_plan* plan, const void* staging, void* stream);
 
-/* Fused pack + replica exchange (replaces strategies.py:88-140 / group_utils.py:342-375 for the
- * sharded layout): tile destinations are spread over `n_peers` staging buffers (peer-mapped device
- * memory reachable over NVLink, own rank included) in equal contiguous shards of the packed byte
- * range: shard j = [j*shard_bytes, (j+1)*shard_bytes) goes to peer_bases[j] + slot_offset.
- * shard_bytes must be a multiple of the plan's tile_bytes/2. */
-int nvrx_pack_sharded(nvrx_plan* plan, void* const* peer_bases, int n_peers, uint64_t shard_bytes,
+/* Fused pack + sharded replica exchange (the all-to-all layout: every member keeps 1/n of every other member's
+ * snapshot; replaces strategies.py:88-140 / group_utils.py:342-375 for that layout): the packed byte range is cut into
+ * `n_peers` contiguous shards of `shard_bytes` (multiple of 512); shard j = [j*shard_bytes, (j+1)*shard_bytes) is stored
+ * at peer_bases[j] + slot_offset (peer-mapped device memory reached with NVLink P2P stores).  If `staging` is not NULL
+ * the kernel additionally keeps the full packed copy there (own snapshot), reading the source tensors only once. */
+int nvrx_pack_sharded(nvrx_plan* plan, void* staging, void* const* peer_bases, int n_peers, uint64_t shard_bytes,
                       uint64_t slot_offset, void* stream);
 
 /* Fused pack + all-gather (reference-identical full replication, strategies.py:88-140): every packed byte is

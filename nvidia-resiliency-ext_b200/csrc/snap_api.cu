@@ -438,9 +438,10 @@ int nvrx_scatter(nvrx_plan* p, const void* staging, void* stream) {
     return launch<nvrx::kDirScatter>(p, const_cast<uint8_t*>(static_cast<const uint8_t*>(staging)), pm, st);
 }
 
-int nvrx_pack_sharded(nvrx_plan* p, void* const* peer_bases, int n_peers, uint64_t shard_bytes, uint64_t slot_offset,
-                      void* stream) {
+int nvrx_pack_sharded(nvrx_plan* p, void* staging, void* const* peer_bases, int n_peers, uint64_t shard_bytes,
+                      uint64_t slot_offset, void* stream) {
     if (!p || !peer_bases || n_peers < 1 || n_peers > 16) return NVRX_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(staging) & 511u) return NVRX_E_INVALID;
     if (shard_bytes == 0 || (shard_bytes & 511u) || (slot_offset & 511u)) return NVRX_E_INVALID;
     if (shard_bytes * static_cast<uint64_t>(n_peers) < p->staging_bytes) return NVRX_E_INVALID;
     DeviceGuard guard(p->device);
@@ -456,13 +457,14 @@ int nvrx_pack_sharded(nvrx_plan* p, void* const* peer_bases, int n_peers, uint64
     memset(&pm, 0, sizeof(pm));
     pm.n_peers = n_peers;
     pm.mode = nvrx::kPeerShard;
+    pm.own = staging != nullptr;
     pm.shard_bytes = shard_bytes;
     pm.slot_off = slot_offset;
     for (int j = 0; j < n_peers; ++j) {
         if (!peer_bases[j] || (reinterpret_cast<uintptr_t>(peer_bases[j]) & 511u)) return NVRX_E_INVALID;
         pm.bases[j] = static_cast<uint8_t*>(peer_bases[j]);
     }
-    return launch<nvrx::kDirPack>(p, nullptr, pm, st);
+    return launch<nvrx::kDirPack>(p, static_cast<uint8_t*>(staging), pm, st);
 }
 
 int nvrx_snapshot(nvrx_plan* p, void* staging, void* host_dst, uint64_t chunk_bytes, volatile uint64_t* progress,

@@ -44,6 +44,7 @@ struct PeerMap {
     uint64_t slot_off;
     int n_peers;
     int mode;
+    int own;  // kPeerShard only: additionally keep a full copy in the local staging buffer
 };
 constexpr int kPeerShard = 1;
 constexpr int kPeerBroadcast = 2;
@@ -264,13 +265,17 @@ __device__ __forceinline__ void widen_bytes(uint8_t* __restrict__ dst, const uin
 }
 
 // staging address of packed position `pos`
-__device__ __forceinline__ uint8_t* stg_addr(uint8_t* staging, const PeerMap& pm, uint64_t pos, int peer = 0) {
+__device__ __forceinline__ uint8_t* stg_addr(uint8_t* staging, const PeerMap& pm, uint64_t pos, int copy = 0) {
     if (pm.n_peers == 0) return staging + pos;
-    if (pm.mode == kPeerBroadcast) return pm.bases[peer] + pm.slot_off + pos;
+    if (pm.mode == kPeerBroadcast) return pm.bases[copy] + pm.slot_off + pos;
+    if (pm.own && copy == 0) return staging + pos;
     const uint64_t j = pos / pm.shard_bytes;
     return pm.bases[j] + pm.slot_off + (pos - j * pm.shard_bytes);
 }
-__device__ __forceinline__ int n_copies(const PeerMap& pm) { return (pm.n_peers && pm.mode == kPeerBroadcast) ? pm.n_peers : 1; }
+__device__ __forceinline__ int n_copies(const PeerMap& pm) {
+    if (pm.n_peers == 0) return 1;
+    return pm.mode == kPeerBroadcast ? pm.n_peers : (pm.own ? 2 : 1);
+}
 
 // one tile, executed by a thread group
 template <int DIR, int UNROLL>

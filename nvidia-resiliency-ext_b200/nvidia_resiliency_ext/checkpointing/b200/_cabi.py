@@ -118,7 +118,7 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_plan_commit": (_int, [_vp, _vp]),
         "nvrx_pack": (_int, [_vp, _vp, _vp]),
         "nvrx_scatter": (_int, [_vp, _vp, _vp]),
-        "nvrx_pack_sharded": (_int, [_vp, P(_vp), _int, _u64, _u64, _vp]),
+        "nvrx_pack_sharded": (_int, [_vp, _vp, P(_vp), _int, _u64, _u64, _vp]),
         "nvrx_pack_broadcast": (_int, [_vp, P(_vp), _int, _u64, _vp]),
         "nvrx_drain": (_int, [_vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
         "nvrx_snapshot": (_int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]),

@@ -114,10 +114,10 @@ class Plan:
     def scatter(self, staging_ptr: int, stream: int) -> None:
         check(self._lib.nvrx_scatter(self._h, staging_ptr, stream), "nvrx_scatter")
 
-    def pack_sharded(self, peer_bases: Sequence[int], shard_bytes: int, slot_offset: int, stream: int) -> None:
+    def pack_sharded(self, staging_ptr: Optional[int], peer_bases: Sequence[int], shard_bytes: int, slot_offset: int, stream: int) -> None:
         check(
             self._lib.nvrx_pack_sharded(
-                self._h, _ptr_array(peer_bases), len(peer_bases), shard_bytes, slot_offset, stream
+                self._h, staging_ptr, _ptr_array(peer_bases), len(peer_bases), shard_bytes, slot_offset, stream
             ),
             "nvrx_pack_sharded",
         )
