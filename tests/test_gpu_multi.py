@@ -127,3 +127,51 @@ def test_replicated_save_retrieve_restore_full_clique(built_library, shm_dir):
     if world < 4:
         pytest.skip("needs >= 4 GPUs")
     run_ranks(_w_replicated_save_and_restore, world, str(shm_dir), 1, world, tuple(range(1, world)), backend="nccl", timeout=600)
+
+
+def _w_sharded(rank, world, root, mode, kill):
+    import os
+    import time
+
+    os.environ["NVRX_B200_EXCHANGE"] = mode
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
+    from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.sharded_local_manager import ShardedLocalCheckpointManager
+
+    mgr = ShardedLocalCheckpointManager.from_replication_params(root, replication_jump=1, replication_factor=world)
+    n = world - 1
+    q = AsyncCallsQueue(persistent=False)
+    for it in (1, 2):
+        sd = BasicTensorAwareStateDict(rank_state(rank + 10 * it))
+        live = list(sd.tensors)
+        req = mgr.save(sd, it, is_async=True)
+        q.schedule_async_request(req)
+        for t in live:
+            t.zero_()
+        assert q.maybe_finalize_async_calls(blocking=True, no_dist=False) == [it - 1]
+    assert SnapshotEngine.get().last_exchange == ("nccl-alltoall" if mode == "nccl" else "p2p-fused-sharded")
+    time.sleep(0.5)
+    files = sorted(p.name for p in mgr.local_ckpt_dir.iterdir())
+    want = [f"iter_0000002_{rank}_local.pt"] + [f"iter_0000002_{m}_local.s{mgr._others(m).index(rank)}of{n}.pt" for m in range(world) if m != rank]
+    assert files == sorted(want), (files, want)
+    dist.barrier()
+    if rank in kill:
+        for p in mgr.local_ckpt_dir.iterdir():
+            p.unlink()
+    dist.barrier()
+    mgr2 = ShardedLocalCheckpointManager(root, clique=mgr.clique)
+    assert mgr2.find_latest() == 2
+    loaded, cid = mgr2.load()
+    want_t = flat_tensors(rank_state(rank + 20))
+    got = list(loaded.tensors)
+    assert cid == (2, rank, "") and len(got) == len(want_t) and all(a.is_cuda and bit_equal(a, b) for a, b in zip(got, want_t))
+    q.close()
+
+
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_sharded_manager_all_to_all_and_rebuild(built_library, shm_dir, mode):
+    """North-star layout: 1/(F-1) fragments exchanged with one all-to-all (fused into the pack kernel over NVLink P2P, or
+    NCCL), a member that lost its storage is rebuilt from the fragments with the scatter kernel, bit-exact."""
+    world = min(torch.cuda.device_count(), 8)
+    run_ranks(_w_sharded, world, str(shm_dir / mode), mode, (world - 1,), backend="nccl")

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--factor", type=int, default=0, help="replication factor (default: world size)")
+    ap.add_argument("--layout", default="full", choices=["full", "sharded"],
+                    help="full = reference semantics (every member stores every member's shard); sharded = striped fragments (all-to-all)")
     args = ap.parse_args()
     os.environ["NVRX_B200_EXCHANGE"] = args.mode
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -45,8 +47,14 @@ def main():
     if rank == 0:
         shutil.rmtree(root, ignore_errors=True)
     dist.barrier()
-    strat = CliqueReplicationStrategy.from_replication_params(1, factor)
-    mgr = LocalCheckpointManager(root, repl_strategy=strat)
+    if args.layout == "sharded":
+        from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.sharded_local_manager import ShardedLocalCheckpointManager
+
+        mgr = ShardedLocalCheckpointManager.from_replication_params(root, replication_jump=1, replication_factor=factor)
+        strat = None
+    else:
+        strat = CliqueReplicationStrategy.from_replication_params(1, factor)
+        mgr = LocalCheckpointManager(root, repl_strategy=strat)
     q = AsyncCallsQueue(persistent=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rows = []
@@ -75,7 +83,10 @@ def main():
         for p in mgr.local_ckpt_dir.iterdir():
             p.unlink()
     dist.barrier()
-    mgr2 = LocalCheckpointManager(root, repl_strategy=strat)
+    if args.layout == "sharded":
+        mgr2 = ShardedLocalCheckpointManager(root, clique=mgr.clique)
+    else:
+        mgr2 = LocalCheckpointManager(root, repl_strategy=strat)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     latest = mgr2.find_latest()
@@ -92,9 +103,10 @@ def main():
     dist.barrier()
     if rank == 0:
         shutil.rmtree(root, ignore_errors=True)
-        nv_bytes = (factor - 1) * total
+        nv_bytes = total if args.layout == "sharded" else (factor - 1) * total
         print(json.dumps({
-            "config": f"C4/C5: LocalCheckpointManager + CliqueReplicationStrategy(J=1, F={factor}) on {world} GPUs, {total/1e9:.2f} GB/rank (scale {args.scale})",
+            "config": f"C4/C5 [{args.layout}]: {'ShardedLocalCheckpointManager' if args.layout == 'sharded' else 'LocalCheckpointManager + CliqueReplicationStrategy'}"
+                      f"(J=1, F={factor}) on {world} GPUs, {total/1e9:.2f} GB/rank (scale {args.scale})",
             "exchange": mode, "save_call_ms": round(t_call * 1e3, 2), "stall_ms_wall": round(t_stall * 1e3, 2), "stall_ms_gpu": round(gpu_ms, 2),
             "nvlink_out_bytes_per_gpu": nv_bytes, "nvlink_GBps_per_gpu_during_stall": round(nv_bytes / (gpu_ms * 1e-3) / 1e9, 1),
             "replicas_persisted_s": round(t_done, 2), "restore_lost_shard_s": round(t_restore, 2), "bit_exact": bool(okt.item()),

@@ -16,12 +16,12 @@ if [[ $WHAT == multi ]]; then
   tail -30 gpurun_out/pytest_multi.log
 fi
 if [[ $WHAT == repl ]]; then
-  NG=${2:-2}; SCALE=${3:-1.0}
-  for MODE in p2p nccl; do
+  NG=${2:-2}; SCALE=${3:-1.0}; LAYOUTS=${4:-"full sharded"}
+  for LAYOUT in $LAYOUTS; do for MODE in p2p nccl; do
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2961$NG \
-        tools/bench_replicate.py --scale $SCALE --mode $MODE --iters 3 > gpurun_out/repl_${NG}_${MODE}.json 2> gpurun_out/repl_${NG}_${MODE}.err
-    tail -2 gpurun_out/repl_${NG}_${MODE}.err; cat gpurun_out/repl_${NG}_${MODE}.json
-  done
+        tools/bench_replicate.py --scale $SCALE --mode $MODE --layout $LAYOUT --iters 3 > gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.json 2> gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.err
+    tail -2 gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.err; cat gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.json
+  done; done
 fi
 if [[ $WHAT == scale ]]; then
   NG=${2:-2}
