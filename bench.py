@@ -265,6 +265,24 @@ def run_engine(args, rank, world, local):
                 a.numel() == 0 or torch.equal(a.contiguous().view(-1).view(torch.uint8), want.contiguous().view(-1).view(torch.uint8)))
         check = "bit-exact" if ok else "MISMATCH"
         del loaded, lt
+    # restore (C5 on one GPU): file -> mmap -> parallel gather into the pinned slot -> ONE H2D -> ONE scatter kernel
+    restore_s = None
+    if not args.no_restore:
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        loaded = torch.load(path, weights_only=False, mmap=True)
+        lt = flatten(loaded)
+        widen = [torch.float32 if (args.narrow and t.dtype == torch.bfloat16) else None for t in lt]
+        back = engine.restore(lt, widen_to=widen if args.narrow else None)
+        torch.cuda.synchronize()
+        restore_s = max_over_ranks(time.perf_counter() - t0)
+        launches += 1
+        if not args.narrow:
+            for a, b in list(zip(back, tensors))[:: max(1, len(tensors) // 32)]:
+                if not torch.equal(a.view(-1).view(torch.uint8), b.view(-1).view(torch.uint8)):
+                    check = "MISMATCH(restore)"
+        del loaded, lt, back
     ckpt.close()
     shutil.rmtree(out_dir, ignore_errors=True)
 
@@ -306,6 +324,8 @@ def run_engine(args, rank, world, local):
         "stall_ms": round(stall_ms, 3),
         "persist_s": round(persist_s, 3),
         "persist_GBps": round(world * total / persist_s / 1e9, 2),
+        "restore_s": None if restore_s is None else round(restore_s, 3),
+        "restore_GBps": None if restore_s is None else round(world * total / restore_s / 1e9, 2),
         "gpu_launches": launches,
         "roofline": {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -414,6 +434,7 @@ def main():
     ap.add_argument("--baseline-sample-gb", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-restore", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram read+write bytes per launch from the ncu capture")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else max(args.warmup, 1)

@@ -185,6 +185,11 @@ int nvrx_hostbuf_write_fd(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int
  * (torch.serialization.skip_data) and the extents fill them in in parallel. */
 int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, const uint64_t* nbytes,
                            const uint64_t* file_offs, int fd, int threads);
+/* Restore-side mirror: copy n host ranges (e.g. tensors of a loaded / mmapped checkpoint file) into the payload at
+ * dst_offsets with `threads` memcpy workers, so ONE H2D + ONE scatter kernel can follow (replaces the N pageable
+ * per-tensor H2D copies of local/basic_state_dict.py:184-187). */
+int nvrx_hostbuf_gather(nvrx_hostbuf* hb, int64_t n, const void* const* srcs, const uint64_t* nbytes,
+                        const uint64_t* dst_offsets, int threads);
 /* crc32 (zlib polynomial) of a payload range computed with `threads` workers and combined. */
 int nvrx_hostbuf_crc32(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int threads, uint32_t* out);
 

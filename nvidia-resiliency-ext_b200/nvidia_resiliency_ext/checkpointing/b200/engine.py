@@ -294,6 +294,12 @@ class HostBuffer:
             "nvrx_hostbuf_writev_fd",
         )
 
+    def gather(self, src_ptrs: Sequence[int], nbytes: Sequence[int], dst_offsets: Sequence[int], threads: int = 16) -> None:
+        check(
+            self._lib.nvrx_hostbuf_gather(self._h, len(src_ptrs), _ptr_array(src_ptrs), _u64_array(nbytes), _u64_array(dst_offsets), threads),
+            "nvrx_hostbuf_gather",
+        )
+
     def crc32(self, offset: int, nbytes: int, threads: int = 8) -> int:
         out = C.c_uint32()
         check(self._lib.nvrx_hostbuf_crc32(self._h, offset, nbytes, threads, C.byref(out)), "nvrx_hostbuf_crc32")
@@ -479,6 +485,7 @@ class SnapshotEngine:
         self._slots = [_Slot(i) for i in range(max(1, host_slots))]
         self._slot_gen = 0
         self.launches = 0  # kernels launched by this engine (pack + scatter)
+        self._pid = os.getpid()  # forked writers inherit this object; only the creator may tear it down
 
     # ---- singletons per device ------------------------------------------------------------------
     @classmethod
@@ -665,13 +672,11 @@ class SnapshotEngine:
         try:
             # gather the CPU tensors into the pinned slot at the plan's offsets (no-op cost when the
             # tensors already are views of one packed buffer with this layout)
-            hbuf = slot.buf.as_tensor(plan.staging_bytes)
-            for t, off, nb in zip(host_tensors, plan.offsets, plan.packed_nbytes):
-                if nb:
-                    src = t.contiguous().view(-1).view(torch.uint8)
-                    dst = hbuf[off : off + nb]
-                    if src.data_ptr() != dst.data_ptr():
-                        dst.copy_(src)
+            srcs = [t if t.is_contiguous() else t.contiguous() for t in host_tensors]
+            base = slot.buf.data_ptr
+            todo = [(s.data_ptr(), nb, off) for s, off, nb in zip(srcs, plan.offsets, plan.packed_nbytes) if nb and s.data_ptr() != base + off]
+            if todo:
+                slot.buf.gather([x[0] for x in todo], [x[1] for x in todo], [x[2] for x in todo], threads=self.prefault_threads or 8)
             stream = self._current_stream()
             if self._staging_free is not None:
                 stream_wait_event(stream, self._staging_free)
@@ -695,6 +700,8 @@ class SnapshotEngine:
         self.launches += 1 if plan.n_tiles else 0
 
     def close(self) -> None:
+        if os.getpid() != self._pid:
+            return
         for plan in self._plans.values():
             plan.close()
         self._plans.clear()
@@ -710,6 +717,18 @@ class SnapshotEngine:
         if self._staging is not None:
             self._staging.close()
             self._staging = None
+        for ptr in [p for pm in getattr(self, "_peer_maps", {}).values() for p in pm["imported"]]:
+            self.lib.nvrx_ipc_close(self.device, ptr)
+        self._peer_maps = {}
+        xbuf = getattr(self, "_exchange_buf", None)
+        if xbuf is not None:
+            xbuf.close()
+            self._exchange_buf = None
+
+
+import atexit  # noqa: E402
+
+atexit.register(SnapshotEngine.shutdown_all)  # unlink the shm slots of a normally exiting trainer
 
 
 def open_snapshot_views(desc: dict, timeout_ms: int = -1) -> Tuple[HostBuffer, List[torch.Tensor]]:

@@ -155,3 +155,24 @@ def test_writer_side_of_a_snapshot_in_process_and_spawned(built_library, tmp_pat
     got = torch.load(tmp_path / "spawned.pt")
     assert torch.equal(got["model"]["a"], a) and torch.equal(got["opt"][0], b)
     hb.close()
+
+
+def test_parallel_gather_into_slot(built_library):
+    hb = make_hb(8 << 20)
+    g = torch.Generator().manual_seed(3)
+    srcs = [torch.randint(0, 255, (n,), dtype=torch.uint8, generator=g) for n in (0, 1, 4097, 3_000_000, 5)]
+    offs, cur = [], 0
+    for t in srcs:
+        cur = (cur + 511) // 512 * 512
+        offs.append(cur)
+        cur += t.numel()
+    hb.gather([t.data_ptr() for t in srcs], [t.numel() for t in srcs], offs, threads=5)
+    view = hb.as_tensor(cur)
+    for t, off in zip(srcs, offs):
+        assert torch.equal(view[off : off + t.numel()], t)
+    from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
+
+    with pytest.raises(SnapError):
+        hb.gather([srcs[3].data_ptr()], [3_000_000], [hb.capacity - 10], threads=2)  # would run past the slot
+    del view
+    hb.close()
