@@ -87,6 +87,12 @@ int nvrx_plan_layout(const nvrx_plan* plan, uint64_t* offsets, uint64_t* packed_
  * restore, or re-allocated parameters).  Alignment classes may change; the tile list is rebuilt. */
 int nvrx_plan_update_ptrs(nvrx_plan* plan, const void* const* ptrs);
 int nvrx_plan_set_variant(nvrx_plan* plan, int variant);
+/* Introspection (tests, tooling): the tile work-list a launch would walk -- tiles [0, *n_bulk) are the TMA-eligible ones,
+ * the rest ragged; up to `capacity` entries are written to seg/nbytes/off (any may be NULL).  `shard_bytes` != 0 shows
+ * the list as nvrx_pack_sharded would build it (tiles never straddle a shard boundary).  No CUDA call is made: the
+ * planner (create / layout / update_ptrs / tiles) works on a machine without a GPU. */
+int nvrx_plan_tiles(const nvrx_plan* plan, uint64_t shard_bytes, uint32_t* n_bulk, uint32_t* n_tiles, uint32_t* seg,
+                    uint32_t* nbytes, uint64_t* off, uint64_t capacity);
 /* Upload descriptor tables if dirty (otherwise done lazily by the first pack/scatter). */
 int nvrx_plan_commit(nvrx_plan* plan, void* stream);
 

@@ -65,15 +65,19 @@ struct nvrx_plan {
     // sharding of the packed range for the fused exchange (0 = none)
     uint64_t shard_bytes = 0;
 
-    // descriptor tables: host mirror (pinned) and device copy
-    SegDesc* h_segs = nullptr;
-    TileDesc* h_tiles = nullptr;
+    // descriptor tables.  The planner itself never touches CUDA (so its logic is testable without a GPU): host
+    // vectors are authoritative, the pinned upload mirror and the device copy are created by the first upload.
+    std::vector<SegDesc> h_segs;
+    std::vector<TileDesc> h_tiles;  // [0,n_bulk) bulk, [n_bulk,n_tiles) ragged
+    SegDesc* pin_segs = nullptr;
+    TileDesc* pin_tiles = nullptr;
     SegDesc* d_segs = nullptr;
     TileDesc* d_tiles = nullptr;
-    size_t tiles_cap = 0;  // capacity (entries) of h_tiles / d_tiles
+    size_t segs_cap = 0, tiles_cap = 0;  // capacity (entries) of the pinned / device mirrors
     uint32_t n_bulk = 0, n_tiles = 0;
     bool segs_dirty = true, tiles_dirty = true;
     std::vector<cudaEvent_t> chunk_events;  // pack -> drain hand-off of the pipelined snapshot
+    cudaEvent_t upload_done = nullptr;      // last H2D of the descriptor mirrors (they are reused)
 };
 
 namespace {
@@ -122,19 +126,10 @@ int build_tiles(nvrx_plan* p) {
     }
     const size_t total = bulk.size() + ragged.size();
     if (total > 0xffffffffull) return NVRX_E_INVALID;
-    if (total > p->tiles_cap) {
-        const size_t cap = std::max<size_t>(total + total / 8, 64);
-        if (p->h_tiles) cudaFreeHost(p->h_tiles);
-        if (p->d_tiles) cudaFree(p->d_tiles);
-        p->h_tiles = nullptr;
-        p->d_tiles = nullptr;
-        p->tiles_cap = 0;
-        NVRX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_tiles), cap * sizeof(TileDesc)));
-        NVRX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_tiles), cap * sizeof(TileDesc)));
-        p->tiles_cap = cap;
-    }
-    if (!bulk.empty()) memcpy(p->h_tiles, bulk.data(), bulk.size() * sizeof(TileDesc));
-    if (!ragged.empty()) memcpy(p->h_tiles + bulk.size(), ragged.data(), ragged.size() * sizeof(TileDesc));
+    p->h_tiles.clear();
+    p->h_tiles.reserve(total);
+    p->h_tiles.insert(p->h_tiles.end(), bulk.begin(), bulk.end());
+    p->h_tiles.insert(p->h_tiles.end(), ragged.begin(), ragged.end());
     p->n_bulk = static_cast<uint32_t>(bulk.size());
     p->n_tiles = static_cast<uint32_t>(total);
     p->tiles_dirty = true;
@@ -142,6 +137,7 @@ int build_tiles(nvrx_plan* p) {
 }
 
 void fill_segs(nvrx_plan* p) {
+    p->h_segs.resize(static_cast<size_t>(p->n));
     for (int64_t i = 0; i < p->n; ++i) {
         SegDesc& s = p->h_segs[i];
         s.ptr = p->ptrs[i];
@@ -154,15 +150,48 @@ void fill_segs(nvrx_plan* p) {
 }
 
 int upload(nvrx_plan* p, cudaStream_t st) {
+    if (p->sm_count == 0) NVRX_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    if (!(p->segs_dirty && p->n > 0) && !(p->tiles_dirty && p->n_tiles > 0)) {
+        p->segs_dirty = p->tiles_dirty = false;
+        return NVRX_OK;
+    }
+    // the pinned mirrors are about to be rewritten: an earlier upload must have finished reading them
+    if (p->upload_done) NVRX_CUDA(cudaEventSynchronize(p->upload_done));
+    else NVRX_CUDA(cudaEventCreateWithFlags(&p->upload_done, cudaEventDisableTiming));
     if (p->segs_dirty && p->n > 0) {
-        NVRX_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, static_cast<size_t>(p->n) * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+        const size_t n = static_cast<size_t>(p->n);
+        if (n > p->segs_cap) {
+            if (p->pin_segs) cudaFreeHost(p->pin_segs);
+            if (p->d_segs) cudaFree(p->d_segs);
+            p->pin_segs = nullptr;
+            p->d_segs = nullptr;
+            p->segs_cap = 0;
+            NVRX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->pin_segs), n * sizeof(SegDesc)));
+            NVRX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_segs), n * sizeof(SegDesc)));
+            p->segs_cap = n;
+        }
+        memcpy(p->pin_segs, p->h_segs.data(), n * sizeof(SegDesc));
+        NVRX_CUDA(cudaMemcpyAsync(p->d_segs, p->pin_segs, n * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
     }
     p->segs_dirty = false;
     if (p->tiles_dirty && p->n_tiles > 0) {
-        NVRX_CUDA(cudaMemcpyAsync(p->d_tiles, p->h_tiles, static_cast<size_t>(p->n_tiles) * sizeof(TileDesc),
-                                  cudaMemcpyHostToDevice, st));
+        const size_t n = p->n_tiles;
+        if (n > p->tiles_cap) {
+            const size_t cap = std::max<size_t>(n + n / 8, 64);
+            if (p->pin_tiles) cudaFreeHost(p->pin_tiles);
+            if (p->d_tiles) cudaFree(p->d_tiles);
+            p->pin_tiles = nullptr;
+            p->d_tiles = nullptr;
+            p->tiles_cap = 0;
+            NVRX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->pin_tiles), cap * sizeof(TileDesc)));
+            NVRX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_tiles), cap * sizeof(TileDesc)));
+            p->tiles_cap = cap;
+        }
+        memcpy(p->pin_tiles, p->h_tiles.data(), n * sizeof(TileDesc));
+        NVRX_CUDA(cudaMemcpyAsync(p->d_tiles, p->pin_tiles, n * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
     }
     p->tiles_dirty = false;
+    NVRX_CUDA(cudaEventRecord(p->upload_done, st));
     return NVRX_OK;
 }
 
@@ -297,20 +326,12 @@ int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes,
         if ((f & NVRX_SEG_NARROW_F32_BF16) && ((nbytes[i] & 3u) || (reinterpret_cast<uintptr_t>(ptrs[i]) & 3u)))
             return NVRX_E_INVALID;
     }
-    DeviceGuard guard(device);
-    if (!guard.ok) return static_cast<int>(cudaErrorInvalidDevice);
-
     nvrx_plan* p = new (std::nothrow) nvrx_plan();
     if (!p) return NVRX_E_NOMEM;
     p->device = device;
     p->n = n;
     p->align = align;
     p->tile_bytes = tile_bytes;
-    int rc = static_cast<int>(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device));
-    if (rc) {
-        delete p;
-        return rc;
-    }
     p->ptrs.resize(n);
     p->nbytes.assign(nbytes, nbytes + n);
     p->flags.resize(n);
@@ -332,13 +353,8 @@ int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes,
     p->staging_bytes = round_up(cur, align);
     p->algo_bytes = src_total + packed_total;
 
-    const size_t seg_cap = static_cast<size_t>(std::max<int64_t>(n, 1));
-    rc = static_cast<int>(cudaMallocHost(reinterpret_cast<void**>(&p->h_segs), seg_cap * sizeof(SegDesc)));
-    if (!rc) rc = static_cast<int>(cudaMalloc(reinterpret_cast<void**>(&p->d_segs), seg_cap * sizeof(SegDesc)));
-    if (!rc) {
-        fill_segs(p);
-        rc = build_tiles(p);
-    }
+    fill_segs(p);
+    int rc = build_tiles(p);
     if (rc) {
         nvrx_plan_destroy(p);
         return rc;
@@ -349,11 +365,14 @@ int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes,
 
 int nvrx_plan_destroy(nvrx_plan* p) {
     if (!p) return NVRX_OK;
-    DeviceGuard guard(p->device);
-    if (p->h_segs) cudaFreeHost(p->h_segs);
-    if (p->h_tiles) cudaFreeHost(p->h_tiles);
-    if (p->d_segs) cudaFree(p->d_segs);
-    if (p->d_tiles) cudaFree(p->d_tiles);
+    if (p->pin_segs || p->pin_tiles || p->d_segs || p->d_tiles || !p->chunk_events.empty() || p->upload_done) {
+        DeviceGuard guard(p->device);
+        if (p->upload_done) cudaEventDestroy(p->upload_done);
+        if (p->pin_segs) cudaFreeHost(p->pin_segs);
+        if (p->pin_tiles) cudaFreeHost(p->pin_tiles);
+        if (p->d_segs) cudaFree(p->d_segs);
+        if (p->d_tiles) cudaFree(p->d_tiles);
+    }
     for (cudaEvent_t ev : p->chunk_events) cudaEventDestroy(ev);
     delete p;
     return NVRX_OK;
@@ -386,9 +405,35 @@ int nvrx_plan_update_ptrs(nvrx_plan* p, const void* const* ptrs) {
         if (((np ^ p->ptrs[i]) & 15u) != 0) same_class = false;
     }
     for (int64_t i = 0; i < p->n; ++i) p->ptrs[i] = reinterpret_cast<uint64_t>(ptrs[i]);
-    DeviceGuard guard(p->device);
     fill_segs(p);
     if (!same_class) return build_tiles(p);
+    return NVRX_OK;
+}
+
+int nvrx_plan_tiles(const nvrx_plan* p, uint64_t shard_bytes, uint32_t* n_bulk, uint32_t* n_tiles, uint32_t* seg, uint32_t* nbytes,
+                    uint64_t* off, uint64_t capacity) {
+    if (!p) return NVRX_E_INVALID;
+    const nvrx_plan* src = p;
+    nvrx_plan tmp;
+    if (shard_bytes != p->shard_bytes) {  // what-if view with another sharding (does not modify the plan)
+        tmp.n = p->n;
+        tmp.tile_bytes = p->tile_bytes;
+        tmp.ptrs = p->ptrs;
+        tmp.nbytes = p->nbytes;
+        tmp.off = p->off;
+        tmp.flags = p->flags;
+        tmp.shard_bytes = shard_bytes;
+        int rc = build_tiles(&tmp);
+        if (rc) return rc;
+        src = &tmp;
+    }
+    if (n_bulk) *n_bulk = src->n_bulk;
+    if (n_tiles) *n_tiles = src->n_tiles;
+    for (uint64_t i = 0; i < src->n_tiles && i < capacity; ++i) {
+        if (seg) seg[i] = src->h_tiles[i].seg;
+        if (nbytes) nbytes[i] = src->h_tiles[i].nbytes;
+        if (off) off[i] = src->h_tiles[i].off;
+    }
     return NVRX_OK;
 }
 

@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "nvrx_plan_layout",
     "nvrx_plan_update_ptrs",
     "nvrx_plan_set_variant",
+    "nvrx_plan_tiles",
     "nvrx_plan_commit",
     "nvrx_pack",
     "nvrx_scatter",
@@ -116,6 +117,7 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_plan_layout": (_int, [_vp, P(_u64), P(_u64)]),
         "nvrx_plan_update_ptrs": (_int, [_vp, P(_vp)]),
         "nvrx_plan_set_variant": (_int, [_vp, _int]),
+        "nvrx_plan_tiles": (_int, [_vp, _u64, P(_u32), P(_u32), P(_u32), P(_u32), P(_u64), _u64]),
         "nvrx_plan_commit": (_int, [_vp, _vp]),
         "nvrx_pack": (_int, [_vp, _vp, _vp]),
         "nvrx_scatter": (_int, [_vp, _vp, _vp]),

@@ -95,6 +95,15 @@ class Plan:
         check(self._lib.nvrx_plan_info(self._h, None, C.byref(tiles), None), "nvrx_plan_info")
         return tiles.value
 
+    def tiles(self, shard_bytes: int = 0):
+        """(n_bulk, [(seg, nbytes, off), ...]) -- the work-list as the kernels would walk it (no CUDA involved)."""
+        nb, nt = C.c_uint32(), C.c_uint32()
+        check(self._lib.nvrx_plan_tiles(self._h, shard_bytes, C.byref(nb), C.byref(nt), None, None, None, 0), "nvrx_plan_tiles")
+        n = nt.value
+        seg, nby, off = (C.c_uint32 * max(n, 1))(), (C.c_uint32 * max(n, 1))(), (C.c_uint64 * max(n, 1))()
+        check(self._lib.nvrx_plan_tiles(self._h, shard_bytes, C.byref(nb), C.byref(nt), seg, nby, off, n), "nvrx_plan_tiles")
+        return nb.value, [(seg[i], nby[i], off[i]) for i in range(n)]
+
     def set_variant(self, variant: int) -> None:
         check(self._lib.nvrx_plan_set_variant(self._h, variant), "nvrx_plan_set_variant")
 

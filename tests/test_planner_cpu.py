@@ -1,0 +1,109 @@
+"""The planner of libnvrx_snap.so (layout + tile work-list) runs without CUDA: check it against the oracle's layout rule and
+against first principles -- every source byte is covered exactly once, bulk tiles are TMA-legal, sharded tile lists never
+straddle a shard boundary.  (The kernels that walk these lists are tested on the GPU.)"""
+import random
+
+import pytest
+
+from oracle import snapshot_oracle as orc
+
+
+def plan_for(ptrs, nbytes, flags=None, **kw):
+    from nvidia_resiliency_ext.checkpointing.b200.engine import Plan
+
+    return Plan(ptrs, nbytes, flags, device=0, **kw)
+
+
+def check_cover(plan, ptrs, nbytes, flags, tile_bytes, shard_bytes=0):
+    n_bulk, tiles = plan.tiles(shard_bytes)
+    covered = [[] for _ in nbytes]
+    for idx, (seg, nb, off) in enumerate(tiles):
+        assert 0 < nb <= tile_bytes and off + nb <= nbytes[seg]
+        narrow = bool(flags and flags[seg])
+        if idx < n_bulk:
+            assert not narrow and nb % 16 == 0 and nb >= 1024 and (ptrs[seg] + off) % 16 == 0  # what cp.async.bulk needs
+        if shard_bytes:
+            scale = 2 if narrow else 1
+            lo = plan.offsets[seg] + off // scale
+            hi = plan.offsets[seg] + (off + nb) // scale
+            assert lo // shard_bytes == (hi - 1) // shard_bytes, "tile straddles a shard boundary"
+        covered[seg].append((off, off + nb))
+    for seg, spans in enumerate(covered):
+        spans.sort()
+        cur = 0
+        for lo, hi in spans:
+            assert lo == cur, f"segment {seg}: gap or overlap at {lo} (expected {cur})"
+            cur = hi
+        assert cur == nbytes[seg]
+    # both lists are sorted by staging position (the pipelined snapshot bisects them)
+    pos = lambda t: plan.offsets[t[0]] + (t[2] // 2 if (flags and flags[t[0]]) else t[2])  # noqa: E731
+    assert [pos(t) for t in tiles[:n_bulk]] == sorted(pos(t) for t in tiles[:n_bulk])
+    assert [pos(t) for t in tiles[n_bulk:]] == sorted(pos(t) for t in tiles[n_bulk:])
+    return n_bulk, tiles
+
+
+@pytest.mark.parametrize("tile_bytes", [4096, 32768, 65536])
+def test_layout_and_tiles_random(built_library, tile_bytes):
+    rng = random.Random(tile_bytes)
+    for trial in range(30):
+        n = rng.randint(0, 60)
+        nbytes = [rng.choice([0, 1, 4, 15, 16, 100, 1023, 1024, 1040, 4096, 32768, 32784, 100_000, 1 << 20]) for _ in range(n)]
+        ptrs = [(0x7F0000000000 + i * (4 << 20) + rng.choice([0, 0, 0, 4, 8, 2, 1])) if nb else 0 for i, nb in enumerate(nbytes)]
+        flags = [1 if (nb % 4 == 0 and ptrs[i] % 4 == 0 and nb and rng.random() < 0.3) else 0 for i, nb in enumerate(nbytes)]
+        align = rng.choice([16, 512, 4096])
+        plan = plan_for(ptrs, nbytes, flags, align=align, tile_bytes=tile_bytes)
+        offs, packed, total = orc.pack_layout(nbytes, [bool(f) for f in flags], align)
+        assert list(plan.offsets) == offs and list(plan.packed_nbytes) == packed and plan.staging_bytes == total
+        assert plan.algorithmic_bytes == sum(nbytes) + sum(packed)
+        check_cover(plan, ptrs, nbytes, flags, tile_bytes)
+        if total:
+            shard = orc.shard_bounds(total, rng.randint(1, 7), 512)[0]
+            check_cover(plan, ptrs, nbytes, flags, tile_bytes, shard_bytes=shard)
+        # re-pointing at tensors with other alignment classes rebuilds the list consistently
+        ptrs2 = [(p + 4 if p and not f else p) for p, f in zip(ptrs, flags)]
+        plan.update_ptrs(ptrs2)
+        check_cover(plan, ptrs2, nbytes, flags, tile_bytes)
+        plan.close()
+
+
+def test_c2_shape_tile_counts(built_library):
+    """The BASELINE C2 state: 1164 large tensors -> bulk tiles only, 291 4-byte steps -> 291 ragged tiles."""
+    from bench import llama3_8b_shard_shapes
+
+    sizes = []
+    for _, shp in llama3_8b_shard_shapes():
+        n = 1
+        for d in shp:
+            n *= d
+        sizes.append(n * 4)
+    nbytes, ptrs, cur = [], [], 0x7E0000000000
+    for nb in sizes:           # model params
+        nbytes.append(nb); ptrs.append(cur); cur += (nb + 511) // 512 * 512
+    for nb in sizes:           # optimizer state: main_param, exp_avg, exp_avg_sq, step
+        for x in (nb, nb, nb, 4):
+            nbytes.append(x); ptrs.append(cur); cur += (x + 511) // 512 * 512
+    assert len(nbytes) == 1455 and sum(nbytes) == 16_060_522_496 + 291 * 4
+    plan = plan_for(ptrs, nbytes)
+    n_bulk, tiles = plan.tiles()
+    assert len(tiles) - n_bulk == 291 and all(t[1] == 4 for t in tiles[n_bulk:])
+    assert n_bulk == sum(-(-nb // 32768) for nb in nbytes if nb > 4)
+    assert plan.staging_bytes == sum((nb + 511) // 512 * 512 for nb in nbytes)
+    plan.close()
+
+
+def test_planner_rejects_bad_arguments(built_library):
+    from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
+
+    for kw in ({"align": 24}, {"align": 8}, {"tile_bytes": 1000}, {"tile_bytes": 1 << 20}):
+        with pytest.raises(SnapError):
+            plan_for([0x1000], [64], None, **kw)
+    with pytest.raises(SnapError):
+        plan_for([0], [64])                      # null pointer with bytes
+    with pytest.raises(SnapError):
+        plan_for([0x1002], [64], [1])            # narrowing needs 4-byte aligned fp32
+    with pytest.raises(SnapError):
+        plan_for([0x1000], [66], [1])            # ... and a multiple of 4 bytes
+    p = plan_for([0x1000, 0], [64, 0])
+    with pytest.raises(SnapError):
+        p.update_ptrs([0, 0])
+    p.close()
