@@ -326,6 +326,20 @@ int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets,
     for (int64_t i = 0; i < n; ++i) first_piece[i + 1] = first_piece[i] + (nbytes[i] + grain - 1) / grain;
     const uint64_t total_pieces = first_piece[n];
     if (total_pieces == 0) return NVRX_OK;
+    // Preferred path: map the destination range and memcpy into it.  pwrite() on tmpfs takes the inode lock, so N
+    // writers to ONE file serialise (measured 3.6 GB/s with 16 threads); page faults on a shared mapping do not.
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!nbytes[i]) continue;
+        lo = std::min(lo, file_offs[i]);
+        hi = std::max(hi, file_offs[i] + nbytes[i]);
+    }
+    const uint64_t map_lo = lo & ~uint64_t(4095);
+    uint8_t* mapped = nullptr;
+    if (!getenv("NVRX_B200_WRITE_PWRITE")) {
+        void* m = mmap(nullptr, hi - map_lo, PROT_READ | PROT_WRITE, MAP_SHARED, fd, static_cast<off_t>(map_lo));
+        if (m != MAP_FAILED) mapped = static_cast<uint8_t*>(m);
+    }
     std::atomic<uint64_t> next{0};
     std::atomic<int> err{0};
     auto worker = [&] {
@@ -336,6 +350,10 @@ int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets,
             while (first_piece[ext + 1] <= piece) ++ext;  // pieces are handed out in increasing order per thread
             const uint64_t o = (piece - first_piece[ext]) * grain;
             uint64_t len = std::min<uint64_t>(grain, nbytes[ext] - o), done = 0;
+            if (mapped) {
+                memcpy(mapped + (file_offs[ext] - map_lo) + o, base + offsets[ext] + o, len);
+                continue;
+            }
             while (done < len) {
                 ssize_t w = pwrite(fd, base + offsets[ext] + o + done, len - done, static_cast<off_t>(file_offs[ext] + o + done));
                 if (w < 0) {
@@ -352,6 +370,7 @@ int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets,
     for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
     worker();
     for (auto& th : pool) th.join();
+    if (mapped) munmap(mapped, hi - map_lo);
     if (err.load()) {
         errno = err.load();
         return NVRX_E_SYS;

@@ -97,7 +97,7 @@ def save(obj, f, *args, **kwargs) -> str:
     if start != 0 or not isinstance(name, (str, bytes)):
         raise RuntimeError("fastsave.save needs a path or a file object opened on a named file at offset 0")
     reader = torch._C.PyTorchFileReader(os.fspath(name))
-    fd = os.open(name, os.O_WRONLY) if is_path else f.fileno()
+    fd = os.open(name, os.O_RDWR) if is_path else f.fileno()  # read+write: the writer maps the range
     try:
         by_slot = {}
         for rec, ptr, nbytes in records:

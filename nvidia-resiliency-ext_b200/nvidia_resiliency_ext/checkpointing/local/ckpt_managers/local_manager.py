@@ -108,7 +108,7 @@ class LocalCheckpointManager(BaseCheckpointManager):
         assert ".dirty" in dirty.suffixes
         try:
             logging.info(f"Saving to {str(dirty)}")
-            with open(dirty, "bx") as fh:  # exclusive create: a second writer on this machine must fail
+            with open(dirty, "x+b") as fh:  # exclusive create: a second writer on this machine must fail
                 fastsave.save(state_dict, fh)  # torch.save format; payload by parallel pwrite when it sits in a slot  # nosec B614
             final = self._local_ckpt_path_from_id(ckpt_id, False)
             logging.info(f"Renaming {str(dirty)} to {final}")

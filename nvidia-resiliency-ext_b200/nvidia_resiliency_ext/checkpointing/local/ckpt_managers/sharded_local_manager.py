@@ -215,7 +215,7 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
         self._ensure_dir()
         frag = (spec["iteration"], spec["owner"], spec["k"], spec["n"])
         dirty = self._fragment_path(frag, True)
-        with open(dirty, "bx") as fh:
+        with open(dirty, "x+b") as fh:
             fastsave.save(spec, fh)
         dirty.rename(self._fragment_path(frag, False))
 
