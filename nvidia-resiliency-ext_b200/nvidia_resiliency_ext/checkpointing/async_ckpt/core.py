@@ -453,6 +453,7 @@ class PersistentAsyncCaller(AsyncCaller):
             torch.cuda.set_device(dev)
             torch.empty(1, device=f"cuda:{dev}")
         _set_process_qos(cpu_priority=cpu_priority, io_priority=io_priority)
+        os.environ["NVRX_B200_CACHE_SLOTS"] = "1"  # long-lived writer: keep snapshot slots mapped between saves
 
         def _on_sigterm(signum, frame):
             raise SystemExit(128 + signum)

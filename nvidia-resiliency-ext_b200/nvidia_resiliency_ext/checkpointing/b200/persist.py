@@ -58,6 +58,40 @@ def _materialise(skeleton: Any, views: List[torch.Tensor]) -> Any:
     return skeleton
 
 
+# Slot mappings kept by a long-lived writer (the persistent worker): re-mapping a 16 GB slot for every checkpoint costs
+# millions of page faults and a page-table teardown per save; slots are few and reused by the engine.
+_slot_cache: Dict[str, Any] = {}
+_SLOT_CACHE_MAX = 8
+
+
+class _Borrowed:
+    """A cached HostBuffer handed to code that calls ``close()`` when done: closing a borrowed mapping is a no-op."""
+
+    def __init__(self, hb):
+        self._hb = hb
+
+    def __getattr__(self, name):
+        return getattr(self._hb, name)
+
+    def close(self, unlink=None):
+        return None
+
+
+def open_slot(name: str, cache: bool):
+    from .engine import HostBuffer
+
+    if not cache:
+        return HostBuffer.open(name)
+    hb = _slot_cache.get(name)
+    if hb is None:
+        for stale in [n for n in _slot_cache if not os.path.exists("/dev/shm" + n)]:
+            _slot_cache.pop(stale).close(unlink=False)
+        while len(_slot_cache) >= _SLOT_CACHE_MAX:
+            _slot_cache.pop(next(iter(_slot_cache))).close(unlink=False)
+        hb = _slot_cache[name] = HostBuffer.open(name)
+    return _Borrowed(hb)
+
+
 def wait_for_snapshots(descs) -> list:
     """Map every snapshot slot named in ``descs`` and block (CPU only) until its drain has finished.
     Returns the mapped HostBuffers; keep them alive while tensor views are in use."""
@@ -80,9 +114,13 @@ def save_snapshot_with_torch(skeleton: Any, path, desc: Dict, *save_args, **save
     ``torch.load`` returns tensors that compare equal to the reference's own ``torch.save`` of the CPU copies.
     """
     from . import fastsave
-    from .engine import open_snapshot_views
+    from .engine import host_views
 
-    hb, views = open_snapshot_views(desc, DRAIN_TIMEOUT_MS)
+    # the persistent worker (it sets NVRX_B200_CACHE_SLOTS in its loop) keeps slots mapped between checkpoints; a forked
+    # one-shot child or an inline call maps and unmaps
+    hb = open_slot(desc["shm_name"], cache=os.environ.get("NVRX_B200_CACHE_SLOTS") == "1")
+    hb.wait(desc["progress_target"], DRAIN_TIMEOUT_MS)
+    views = host_views(desc["layout"], hb)
     try:
         obj = _materialise(skeleton, views)
         fast_zip_writes()
