@@ -230,7 +230,7 @@ def run_engine(args, rank, world, local):
     stall, host_safe, persist = [], [], []
     done_ev = torch.cuda.Event()
     for it in range(args.e2e_warmup + args.e2e_steps):
-        path = out_dir / f"ckpt_{it % 2}.pt"
+        path = out_dir / "ckpt.pt"  # one file per rank, overwritten every step (bounds the tmpfs footprint)
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()

@@ -23,7 +23,7 @@ from bench import flatten, llama3_8b_shard_state, max_over_ranks  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--scale", type=float, default=0.25)
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--factor", type=int, default=0, help="replication factor (default: world size)")

@@ -2,6 +2,7 @@
 # One GPU-box visit: tests, bench (both arms), ncu launch list + full capture.  Outputs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
+{ echo "memory.max: $(cat /sys/fs/cgroup/memory.max 2>/dev/null)"; echo "memory.current: $(cat /sys/fs/cgroup/memory.current 2>/dev/null)"; df -h /dev/shm | tail -1; } > gpurun_out/memlimits.txt 2>&1
 WHAT=${1:-all}
 if [[ $WHAT == all || $WHAT == tests ]]; then
   timeout 1500 python -m pytest tests -m gpu -q --durations=15 --timeout=900 > gpurun_out/pytest_gpu.log 2>&1
@@ -16,7 +17,7 @@ if [[ $WHAT == multi ]]; then
   tail -30 gpurun_out/pytest_multi.log
 fi
 if [[ $WHAT == repl ]]; then
-  NG=${2:-2}; SCALE=${3:-1.0}; LAYOUTS=${4:-"full sharded"}
+  NG=${2:-2}; SCALE=${3:-0.25}; LAYOUTS=${4:-"full sharded"}
   for LAYOUT in $LAYOUTS; do for MODE in p2p nccl; do
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2961$NG \
         tools/bench_replicate.py --scale $SCALE --mode $MODE --layout $LAYOUT --iters 3 > gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.json 2> gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.err
@@ -28,6 +29,13 @@ if [[ $WHAT == scale ]]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2962$NG \
       bench.py --gpus $NG > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err
   tail -2 gpurun_out/bench_n$NG.err; cat gpurun_out/bench_n$NG.json
+fi
+if [[ $WHAT == sanitize ]]; then
+  # memcheck over the ragged (funnel / head / tail) paths and both walkers: no out-of-bounds access on odd alignments
+  timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 \
+      python -m pytest tests/test_gpu_parity.py -q -x -k "ragged or roundtrip_into or narrow or degenerate" > gpurun_out/sanitizer_memcheck.log 2>&1
+  echo "memcheck exit code: $?" >> gpurun_out/sanitizer_memcheck.log
+  tail -8 gpurun_out/sanitizer_memcheck.log
 fi
 if [[ $WHAT == ncu_list ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk_ -c 40 --csv --log-file gpurun_out/launches.csv \
