@@ -729,10 +729,11 @@ class SnapshotEngine:
         for ptr in [p for pm in getattr(self, "_peer_maps", {}).values() for p in pm["imported"]]:
             self.lib.nvrx_ipc_close(self.device, ptr)
         self._peer_maps = {}
-        xbuf = getattr(self, "_exchange_buf", None)
-        if xbuf is not None:
-            xbuf.close()
-            self._exchange_buf = None
+        for attr in ("_exchange_buf", "_p2p_buf"):
+            buf = getattr(self, attr, None)
+            if buf is not None:
+                buf.close()
+                setattr(self, attr, None)
 
 
 import atexit  # noqa: E402

@@ -45,21 +45,19 @@ def as_uint8_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
     return torch.as_tensor(_CudaBytes(ptr, max(nbytes, 1)), device=torch.device("cuda", device))[:nbytes]
 
 
-def _exchange_buffer(engine: SnapshotEngine, nbytes: int) -> DeviceBuffer:
-    buf = getattr(engine, "_exchange_buf", None)
+def _private_buffer(engine: SnapshotEngine, nbytes: int) -> DeviceBuffer:
+    """Device scratch for point-to-point payloads (never exported to peers)."""
+    buf = getattr(engine, "_p2p_buf", None)
     if buf is None or buf.nbytes < nbytes:
-        free_ev: Optional[Event] = getattr(engine, "_exchange_free", None)
-        if free_ev is not None:
-            free_ev.synchronize()
-        _drop_peer_maps(engine)
         if buf is not None:
+            torch.cuda.current_stream(engine.device).synchronize()
             buf.close()
         buf = DeviceBuffer(max(nbytes, 512), engine.device)
-        engine._exchange_buf = buf
+        engine._p2p_buf = buf
     return buf
 
 
-# ---- NVLink peer mapping of the exchange buffers (fused pack + all-gather) ---------------------------
+# ---- the clique-shared exchange buffer and its NVLink peer mappings -----------------------------------
 def _drop_peer_maps(engine: SnapshotEngine) -> None:
     for pm in getattr(engine, "_peer_maps", {}).values():
         for ptr in pm["imported"]:
@@ -71,41 +69,54 @@ def _exchange_mode() -> str:
     return os.environ.get("NVRX_B200_EXCHANGE", "auto").lower()  # auto | p2p | nccl
 
 
-def _peer_bases(engine: SnapshotEngine, group, xbuf: DeviceBuffer) -> Optional[List[int]]:
-    """Device addresses of every clique member's exchange buffer as seen from this GPU (own buffer included),
-    or None when the clique cannot use NVLink P2P (members on different hosts, no peer access, or disabled).
-    Collective over ``group`` the first time a given buffer generation is used."""
+def shared_exchange(engine: SnapshotEngine, group, need: int):
+    """Collective over ``group``: the exchange buffer of at least ``need`` bytes on every member and, when the clique
+    is NVLink-peer reachable, the device addresses of every member's buffer as seen from this GPU (own included).
+
+    (Re)allocation is decided collectively and ordered: every member first closes the peer mappings it imported, the
+    clique synchronises, only then buffers are freed / re-allocated and handles re-exchanged -- an exported allocation is
+    never freed while a peer still has it mapped.  Returns ``(buffer, bases or None)``."""
+    have = getattr(engine, "_exchange_buf", None)
+    have_bytes = have.nbytes if have is not None else 0
     mode = _exchange_mode()
-    if mode == "nccl" or group.world_size == 1:
-        return None
+    me = group.my_group_rank
+    infos = group.all_gather_object({"have": have_bytes, "host": socket.gethostname(), "boot": _boot_id(), "dev": engine.device})
+    target = max([need] + [i["have"] for i in infos])
     maps = getattr(engine, "_peer_maps", None)
     if maps is None:
         maps = engine._peer_maps = {}
-    key = (id(group.group), xbuf.ptr, xbuf.nbytes)
-    if key in maps:
-        return maps[key]["bases"]
-    mine = {"host": socket.gethostname(), "boot": _boot_id(), "dev": engine.device, "handle": xbuf.ipc_handle(), "nbytes": xbuf.nbytes}
-    infos = group.all_gather_object(mine)
-    me = group.my_group_rank
-    ok = all(i["host"] == mine["host"] and i["boot"] == mine["boot"] and i["nbytes"] == xbuf.nbytes for i in infos)
-    ok = ok and all(r == me or torch.cuda.can_device_access_peer(engine.device, i["dev"]) for r, i in enumerate(infos))
-    votes = group.all_gather_object(bool(ok))
-    if not all(votes):
-        if mode == "p2p":
-            raise RuntimeError("NVRX_B200_EXCHANGE=p2p but the clique is not NVLink-peer reachable from every member")
-        maps[key] = {"bases": None, "imported": []}
-        return None
-    bases, imported = [], []
-    for r, info in enumerate(infos):
-        if r == me:
-            bases.append(xbuf.ptr)
-            continue
-        out = C.c_void_p()
-        check(engine.lib.nvrx_ipc_import(engine.device, info["handle"], C.byref(out)), "nvrx_ipc_import")
-        bases.append(out.value)
-        imported.append(out.value)
-    maps[key] = {"bases": bases, "imported": imported}
-    return bases
+    key = id(group.group)
+    regen = any(i["have"] != target for i in infos) or key not in maps
+    if regen:
+        free_ev: Optional[Event] = getattr(engine, "_exchange_free", None)
+        if free_ev is not None:
+            free_ev.synchronize()  # my drain of the buffer (which follows every peer's stores into it) is over
+        _drop_peer_maps(engine)
+        group.all_gather_object(None)  # everybody closed its imports: exported buffers may now be freed
+        if have_bytes != target:
+            if have is not None:
+                have.close()
+            have = engine._exchange_buf = DeviceBuffer(max(target, 512), engine.device)
+        p2p_ok = mode != "nccl" and group.world_size > 1
+        p2p_ok = p2p_ok and all(i["host"] == infos[me]["host"] and i["boot"] == infos[me]["boot"] for i in infos)
+        p2p_ok = p2p_ok and all(r == me or torch.cuda.can_device_access_peer(engine.device, i["dev"]) for r, i in enumerate(infos))
+        votes = group.all_gather_object((bool(p2p_ok), have.ipc_handle() if p2p_ok else None))
+        if all(v[0] for v in votes):
+            bases, imported = [], []
+            for r, (_, handle) in enumerate(votes):
+                if r == me:
+                    bases.append(have.ptr)
+                    continue
+                out = C.c_void_p()
+                check(engine.lib.nvrx_ipc_import(engine.device, handle, C.byref(out)), "nvrx_ipc_import")
+                bases.append(out.value)
+                imported.append(out.value)
+            maps[key] = {"bases": bases, "imported": imported}
+        else:
+            if mode == "p2p":
+                raise RuntimeError("NVRX_B200_EXCHANGE=p2p but the clique is not NVLink-peer reachable from every member")
+            maps[key] = {"bases": None, "imported": []}
+    return have, maps[key]["bases"]
 
 
 def _boot_id() -> str:
@@ -144,7 +155,7 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
     plan = engine._plan_for(my_tensors, [False] * len(my_tensors))
     assert list(plan.offsets) == layouts[me][0] and plan.staging_bytes == layouts[me][2]
 
-    xbuf = _exchange_buffer(engine, world * slot_bytes)
+    xbuf, bases = shared_exchange(engine, group, world * slot_bytes)
     stream = engine._current_stream()
     free_ev = getattr(engine, "_exchange_free", None)
     if free_ev is not None:
@@ -152,7 +163,6 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
 
         stream_wait_event(stream, free_ev)  # previous drain of the exchange buffer must be over
     whole = as_uint8_tensor(xbuf.ptr, world * slot_bytes, engine.device)
-    bases = _peer_bases(engine, group, xbuf)
     if bases is not None:
         # fused pack + all-gather: ONE kernel reads the tensors once and stores slice `me` into every member's
         # exchange buffer (own HBM + NVLink P2P).  Barrier 1: every member's previous drain of its buffer is over;
@@ -226,7 +236,7 @@ def send_packed(group, tensors: Sequence[torch.Tensor], dst_global_rank: int) ->
     cuda_tensors = [t if t.is_cuda else t.to(torch.device("cuda", dev)) for t in tensors]
     cuda_tensors = [t.detach() if t.is_contiguous() else t.detach().contiguous() for t in cuda_tensors]
     plan = engine._plan_for(cuda_tensors, [False] * len(cuda_tensors))
-    xbuf = _exchange_buffer(engine, plan.staging_bytes)
+    xbuf = _private_buffer(engine, plan.staging_bytes)
     stream = engine._current_stream()
     plan.pack(xbuf.ptr, stream)
     engine.launches += 1 if plan.n_tiles else 0
@@ -241,7 +251,7 @@ def recv_packed(group, dests: Sequence[torch.Tensor], src_global_rank: int) -> N
     on_dev = [d if d.is_cuda else torch.empty(d.shape, dtype=d.dtype, device=torch.device("cuda", dev)) for d in dests]
     assert all(d.is_contiguous() for d in on_dev)
     plan = engine._plan_for(on_dev, [False] * len(on_dev))
-    xbuf = _exchange_buffer(engine, plan.staging_bytes)
+    xbuf = _private_buffer(engine, plan.staging_bytes)
     dist.recv(as_uint8_tensor(xbuf.ptr, plan.staging_bytes, dev), src_global_rank, group=group.group)
     stream = engine._current_stream()
     plan.scatter(xbuf.ptr, stream)

@@ -305,14 +305,13 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
         me = self.rank
         stream = engine._current_stream()
         staging = engine._ensure_staging(total)
-        xbuf = xch._exchange_buffer(engine, n * frag_slot)
+        xbuf, bases = xch.shared_exchange(engine, self.clique, n * frag_slot)
         if engine._staging_free is not None:
             stream_wait_event(stream, engine._staging_free)
         free_ev = getattr(engine, "_exchange_free", None)
         if free_ev is not None:
             stream_wait_event(stream, free_ev)
 
-        bases = xch._peer_bases(engine, self.clique, xbuf)
         recv_sizes = []
         for m, meta in zip(self._members, metas):
             lo, hi = (0, 0) if m == me else fragment_range(meta["total"], meta["shard_bytes"], self._others(m).index(me))
