@@ -200,7 +200,7 @@ def run_engine(args, rank, world, local):
     dev = torch.device("cuda", local)
     sd, total = llama3_8b_shard_state(dev, seed=1234 + rank, scale=args.scale)
     tensors = flatten(sd)
-    engine = SnapshotEngine.get(local, host_slots=2)
+    engine = SnapshotEngine.get(local, host_slots=2)  # slots are created lazily; sequential steps use one
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- kernel-only: K back-to-back pack launches (value, roofline) -------------------------------
@@ -224,25 +224,41 @@ def run_engine(args, rank, world, local):
     launches = args.steps
 
     # ---- end to end through the public API -----------------------------------------------------------
+    # Host-memory budget: the box's cgroup (200 GiB on the 1-GPU boxes of this pool) also counts tmpfs / POSIX-shm
+    # pages.  One rank needs a 16 GB pinned slot; persisting adds a 16 GB file per rank.  With several ranks on a box
+    # the files would not fit (8 x 32 GB), so N>1 measures the snapshot through utils.preload_tensors (state -> pinned
+    # host, no file) and only N=1 runs the full TorchAsyncCheckpoint.async_save -> file -> restore cycle.
+    persist_files = world == 1 or args.persist
     out_dir = shm_dir(rank)
     engine_launches_before = None
-    ckpt = TorchAsyncCheckpoint(persistent_queue=True, narrow_fp32_to_bf16=args.narrow)
+    ckpt = TorchAsyncCheckpoint(persistent_queue=True, narrow_fp32_to_bf16=args.narrow) if persist_files else None
     stall, host_safe, persist = [], [], []
     done_ev = torch.cuda.Event()
+    path = out_dir / "ckpt.pt"  # one file per rank, overwritten every step
+    from nvidia_resiliency_ext.checkpointing.utils import preload_tensors
+
     for it in range(args.e2e_warmup + args.e2e_steps):
-        path = out_dir / "ckpt.pt"  # one file per rank, overwritten every step (bounds the tmpfs footprint)
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        ckpt.async_save(sd, path)
-        done_ev.record()
-        done_ev.synchronize()  # the training stream is free again here
-        t1 = time.perf_counter()
-        snap = next(iter(ckpt._pending.values()))
-        snap.wait()  # bytes are in host memory
-        t2 = time.perf_counter()
-        ckpt.finalize_async_save(blocking=True, no_dist=True)
-        t3 = time.perf_counter()
+        if persist_files:
+            ckpt.async_save(sd, path)
+            done_ev.record()
+            done_ev.synchronize()  # the training stream is free again here
+            t1 = time.perf_counter()
+            snap = next(iter(ckpt._pending.values()))
+            snap.wait()  # bytes are in host memory
+            t2 = time.perf_counter()
+            ckpt.finalize_async_save(blocking=True, no_dist=True)
+            t3 = time.perf_counter()
+        else:
+            _, snap = preload_tensors(sd, non_blocking=True, narrow=args.narrow, return_snapshot=True)
+            done_ev.record()
+            done_ev.synchronize()
+            t1 = time.perf_counter()
+            snap.wait()
+            t2 = t3 = time.perf_counter()
+            snap.release()
         if it == args.e2e_warmup - 1 or (args.e2e_warmup == 0 and it == 0 and engine_launches_before is None):
             engine_launches_before = engine.launches if args.e2e_warmup else 0
         if it >= args.e2e_warmup:
@@ -255,7 +271,7 @@ def run_engine(args, rank, world, local):
     persist_s = max_over_ranks(median(persist))
     # spot-check the last file against the live state (bit-exact unless narrowed)
     check = "skipped"
-    if rank == 0 and not args.no_verify:
+    if rank == 0 and not args.no_verify and persist_files:
         loaded = torch.load(path, weights_only=False)
         lt = flatten(loaded)
         ok = len(lt) == len(tensors)
@@ -267,7 +283,7 @@ def run_engine(args, rank, world, local):
         del loaded, lt
     # restore (C5 on one GPU): file -> mmap -> parallel gather into the pinned slot -> ONE H2D -> ONE scatter kernel
     restore_s = None
-    if not args.no_restore:
+    if not args.no_restore and persist_files:
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
@@ -283,7 +299,8 @@ def run_engine(args, rank, world, local):
                 if not torch.equal(a.view(-1).view(torch.uint8), b.view(-1).view(torch.uint8)):
                     check = "MISMATCH(restore)"
         del loaded, lt, back
-    ckpt.close()
+    if ckpt is not None:
+        ckpt.close()
     shutil.rmtree(out_dir, ignore_errors=True)
 
     packed_bytes = plan.staging_bytes
@@ -318,12 +335,15 @@ def run_engine(args, rank, world, local):
             "unit": "GB/s",
             "h2d_bytes_per_step": int(len(tensors) * 32),
             "d2h_bytes_per_step": int(packed_bytes),
-            "definition": "state bytes / wall time from TorchAsyncCheckpoint.async_save() until the snapshot is in pinned host memory",
+            "definition": ("state bytes / wall time from TorchAsyncCheckpoint.async_save() until the snapshot is in pinned host memory"
+                           if persist_files else
+                           "state bytes / wall time from checkpointing.utils.preload_tensors() until the snapshot is in pinned host memory "
+                           "(no file at N>1: host-memory budget of the box)"),
             "steps": args.e2e_steps,
         },
         "stall_ms": round(stall_ms, 3),
-        "persist_s": round(persist_s, 3),
-        "persist_GBps": round(world * total / persist_s / 1e9, 2),
+        "persist_s": round(persist_s, 3) if persist_files else None,
+        "persist_GBps": round(world * total / persist_s / 1e9, 2) if persist_files else None,
         "restore_s": None if restore_s is None else round(restore_s, 3),
         "restore_GBps": None if restore_s is None else round(world * total / restore_s / 1e9, 2),
         "gpu_launches": launches,
@@ -435,6 +455,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-restore", action="store_true")
+    ap.add_argument("--persist", action="store_true", help="write checkpoint files at N>1 too (needs ~32 GB of host memory per rank)")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram read+write bytes per launch from the ncu capture")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else max(args.warmup, 1)

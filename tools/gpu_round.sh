@@ -4,35 +4,57 @@ set -u
 mkdir -p gpurun_out
 { echo "memory.max: $(cat /sys/fs/cgroup/memory.max 2>/dev/null)"; echo "memory.current: $(cat /sys/fs/cgroup/memory.current 2>/dev/null)"; df -h /dev/shm | tail -1; } > gpurun_out/memlimits.txt 2>&1
 WHAT=${1:-all}
+
+# Memory guard: the box's cgroup (memory.max, 200 GiB on a 1-GPU box) also counts tmpfs / POSIX-shm pages, i.e. the
+# pinned snapshot slots and the checkpoint files in /dev/shm.  Exceeding it kills the whole box.  Every workload below
+# runs in its own session; a watcher kills that session (only it) and removes our shm files above 70 % of the limit.
+MEM_MAX=$(cat /sys/fs/cgroup/memory.max 2>/dev/null || echo max)
+[[ $MEM_MAX == max ]] && MEM_MAX=$(( $(grep MemTotal /proc/meminfo | awk '{print $2}') * 1024 ))
+MEM_CAP=$(( MEM_MAX / 10 * 7 ))
+guarded() {
+  setsid "$@" &
+  local pid=$!
+  ( while kill -0 $pid 2>/dev/null; do
+      cur=$(cat /sys/fs/cgroup/memory.current 2>/dev/null || echo 0)
+      if (( cur > MEM_CAP )); then
+        echo "MEMORY GUARD: $cur > $MEM_CAP, killing session $pid" >> gpurun_out/memguard.txt
+        kill -TERM -- -$pid 2>/dev/null; sleep 2; kill -KILL -- -$pid 2>/dev/null
+        rm -f /dev/shm/nvrx_* 2>/dev/null; rm -rf /dev/shm/nvrx_b200_* 2>/dev/null
+        break
+      fi
+      sleep 0.5
+    done ) &
+  wait $pid
+}
 if [[ $WHAT == all || $WHAT == tests ]]; then
-  timeout 1500 python -m pytest tests -m gpu -q --durations=15 --timeout=900 > gpurun_out/pytest_gpu.log 2>&1
+  guarded timeout 1500 python -m pytest tests -m gpu -q --durations=15 --timeout=900 > gpurun_out/pytest_gpu.log 2>&1
   tail -25 gpurun_out/pytest_gpu.log
 fi
 if [[ $WHAT == all || $WHAT == bench ]]; then
-  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
-  timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+  guarded timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
+  guarded timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 fi
 if [[ $WHAT == multi ]]; then
-  timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi.log 2>&1
+  guarded timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi.log 2>&1
   tail -30 gpurun_out/pytest_multi.log
 fi
 if [[ $WHAT == repl ]]; then
   NG=${2:-2}; SCALE=${3:-0.25}; LAYOUTS=${4:-"full sharded"}
   for LAYOUT in $LAYOUTS; do for MODE in p2p nccl; do
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2961$NG \
+    guarded timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2961$NG \
         tools/bench_replicate.py --scale $SCALE --mode $MODE --layout $LAYOUT --iters 3 > gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.json 2> gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.err
     tail -2 gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.err; cat gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.json
   done; done
 fi
 if [[ $WHAT == scale ]]; then
   NG=${2:-2}
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2962$NG \
+  guarded timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2962$NG \
       bench.py --gpus $NG > gpurun_out/bench_n$NG.json 2> gpurun_out/bench_n$NG.err
   tail -2 gpurun_out/bench_n$NG.err; cat gpurun_out/bench_n$NG.json
 fi
 if [[ $WHAT == sanitize ]]; then
   # memcheck over the ragged (funnel / head / tail) paths and both walkers: no out-of-bounds access on odd alignments
-  timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 \
+  guarded timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 \
       python -m pytest tests/test_gpu_parity.py -q -x -k "ragged or roundtrip_into or narrow or degenerate" > gpurun_out/sanitizer_memcheck.log 2>&1
   echo "memcheck exit code: $?" >> gpurun_out/sanitizer_memcheck.log
   tail -8 gpurun_out/sanitizer_memcheck.log
