@@ -79,9 +79,10 @@ def main():
     t_call, t_stall, gpu_ms, t_done = (max_over_ranks(sorted(r[i] for r in rows)[len(rows) // 2]) for i in range(4))
     # C5: rank 1 loses its storage, gets its shard back from a replica holder and scatters it
     dist.barrier()
+    time.sleep(1.0)  # let the background cleanup of the previous iteration finish
     if rank == 1 % world:
-        for p in mgr.local_ckpt_dir.iterdir():
-            p.unlink()
+        for p in list(mgr.local_ckpt_dir.iterdir()):
+            p.unlink(missing_ok=True)
     dist.barrier()
     if args.layout == "sharded":
         mgr2 = ShardedLocalCheckpointManager(root, clique=mgr.clique)
