@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--factor", type=int, default=0, help="replication factor (default: world size)")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="time only the fused pack+exchange kernels at the given scale (no host slots, no files)")
     ap.add_argument("--layout", default="full", choices=["full", "sharded"],
                     help="full = reference semantics (every member stores every member's shard); sharded = striped fragments (all-to-all)")
     args = ap.parse_args()
@@ -41,6 +43,8 @@ def main():
     from nvidia_resiliency_ext.checkpointing.local.replication.strategies import CliqueReplicationStrategy
 
     factor = args.factor or world
+    if args.kernel_only:
+        return kernel_only(args, rank, world, local)
     sd, total = llama3_8b_shard_state(torch.device("cuda", local), seed=1234 + rank, scale=args.scale)
     want = [t.clone() for t in flatten(sd)] if args.scale <= 0.3 else None
     root = Path("/dev/shm") / f"nvrx_b200_repl_{os.environ.get('MASTER_PORT', '0')}"
@@ -113,6 +117,87 @@ def main():
             "replicas_persisted_s": round(t_done, 2), "restore_lost_shard_s": round(t_restore, 2), "bit_exact": bool(okt.item()),
             "nccl_ops_on_data_path": 0 if mode == "p2p-fused" else 1, "reference_nccl_ops": f"{factor} x 1455 broadcasts",
         }), flush=True)
+    dist.destroy_process_group()
+
+
+def kernel_only(args, rank, world, local):
+    """C4 at full size without touching host memory: the fused kernels over NVLink, CUDA-event timed, max over ranks."""
+    from nvidia_resiliency_ext.checkpointing.b200 import exchange as xch
+    from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.sharded_local_manager import shard_bytes_for
+    from nvidia_resiliency_ext.checkpointing.local.replication.group_utils import GroupWrapper
+
+    sd, total = llama3_8b_shard_state(torch.device("cuda", local), seed=1234 + rank, scale=args.scale)
+    tensors = flatten(sd)
+    engine = SnapshotEngine.get(local)
+    plan = engine._plan_for(tensors, [False] * len(tensors))
+    S = plan.staging_bytes
+    grp = GroupWrapper()
+    stream = torch.cuda.current_stream().cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {"config": f"C4 kernel-only on {world} GPUs, {total/1e9:.2f} GB/rank (scale {args.scale})", "mode": args.mode}
+
+    def timed(fn):
+        ms = []
+        for it in range(2 + args.iters):
+            xch._clique_barrier(engine, grp)
+            e0.record()
+            fn()
+            e1.record()
+            xch._clique_barrier(engine, grp)
+            e1.synchronize()
+            if it >= 2:
+                ms.append(e0.elapsed_time(e1))
+        return max_over_ranks(sorted(ms)[len(ms) // 2])
+
+    staging = engine._ensure_staging(S)
+    if world > 1:
+        # sharded: own full copy + fragment k -> k-th other member
+        n = world - 1
+        sb = shard_bytes_for(S, n)
+        xbuf, bases = xch.shared_exchange(engine, grp, n * sb)
+        if bases is not None:
+            others = [r for r in range(world) if r != rank]
+            dest = [bases[m] + [r for r in range(world) if r != m].index(rank) * sb for m in others]
+            t = timed(lambda: plan.pack_sharded(staging.ptr, dest, sb, 0, stream))
+            out["sharded_fused_ms"] = round(t, 3)
+            out["sharded_nvlink_GBps_per_gpu"] = round(S / (t * 1e-3) / 1e9, 1)
+            out["sharded_hbm_GBps"] = round(3 * S / (t * 1e-3) / 1e9, 1)  # read S, write S local, S remote
+        whole = xch.as_uint8_tensor(staging.ptr, S, local)
+        recv = xch.as_uint8_tensor(xbuf.ptr, n * sb, local)
+        def frag(k):
+            return min(S, (k + 1) * sb) - min(S, k * sb)
+
+        def idx(owner, holder):  # which fragment of `owner` lives on `holder`
+            return [r for r in range(world) if r != owner].index(holder)
+
+        splits_in = [0 if q == rank else frag(idx(rank, q)) for q in range(world)]
+        splits_out = [0 if q == rank else frag(idx(q, rank)) for q in range(world)]
+
+        def nccl_a2a():
+            plan.pack(staging.ptr, stream)
+            torch.distributed.all_to_all_single(recv[: sum(splits_out)], whole[: sum(splits_in)], splits_out, splits_in)
+        t = timed(nccl_a2a)
+        out["sharded_pack_plus_nccl_alltoall_ms"] = round(t, 3)
+        # full replication: every member gets every member's packed snapshot
+        free, _ = torch.cuda.mem_get_info()
+        if free > world * S + (8 << 30):
+            xbuf, bases = xch.shared_exchange(engine, grp, world * S)
+            if bases is not None:
+                t = timed(lambda: plan.pack_broadcast(bases, rank * S, stream))
+                out["full_fused_ms"] = round(t, 3)
+                out["full_nvlink_GBps_per_gpu"] = round((world - 1) * S / (t * 1e-3) / 1e9, 1)
+            big = xch.as_uint8_tensor(xbuf.ptr, world * S, local)
+            def nccl_ag():
+                plan.pack(xbuf.ptr + rank * S, stream)
+                torch.distributed.all_gather_into_tensor(big, big[rank * S : (rank + 1) * S])
+            t = timed(nccl_ag)
+            out["full_pack_plus_nccl_allgather_ms"] = round(t, 3)
+    t = timed(lambda: plan.pack(staging.ptr, stream))
+    out["local_pack_ms"] = round(t, 3)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.barrier()
     dist.destroy_process_group()
 
 

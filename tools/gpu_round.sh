@@ -46,6 +46,12 @@ if [[ $WHAT == repl ]]; then
     tail -2 gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.err; cat gpurun_out/repl_${NG}_${LAYOUT}_${MODE}.json
   done; done
 fi
+if [[ $WHAT == replk ]]; then
+  NG=${2:-2}; SCALE=${3:-1.0}
+  guarded timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2963$NG \
+      tools/bench_replicate.py --kernel-only --scale $SCALE --iters 5 > gpurun_out/replk_${NG}.json 2> gpurun_out/replk_${NG}.err
+  tail -3 gpurun_out/replk_${NG}.err; cat gpurun_out/replk_${NG}.json
+fi
 if [[ $WHAT == scale ]]; then
   NG=${2:-2}
   guarded timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 2962$NG \
