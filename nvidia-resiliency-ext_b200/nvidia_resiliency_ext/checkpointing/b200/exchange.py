@@ -80,19 +80,20 @@ def shared_exchange(engine: SnapshotEngine, group, need: int):
     have_bytes = have.nbytes if have is not None else 0
     mode = _exchange_mode()
     me = group.my_group_rank
-    infos = group.all_gather_object({"have": have_bytes, "host": socket.gethostname(), "boot": _boot_id(), "dev": engine.device})
-    target = max([need] + [i["have"] for i in infos])
+    haves = group.all_gather_int(have_bytes)  # one small tensor collective per exchange; objects only when regenerating
+    target = max([need] + haves)
     maps = getattr(engine, "_peer_maps", None)
     if maps is None:
         maps = engine._peer_maps = {}
     key = id(group.group)
-    regen = any(i["have"] != target for i in infos) or key not in maps
+    regen = any(h != target for h in haves) or key not in maps
     if regen:
+        infos = group.all_gather_object({"host": socket.gethostname(), "boot": _boot_id(), "dev": engine.device})
         free_ev: Optional[Event] = getattr(engine, "_exchange_free", None)
         if free_ev is not None:
             free_ev.synchronize()  # my drain of the buffer (which follows every peer's stores into it) is over
         _drop_peer_maps(engine)
-        group.all_gather_object(None)  # everybody closed its imports: exported buffers may now be freed
+        group.all_gather_int(0)  # everybody closed its imports: exported buffers may now be freed
         if have_bytes != target:
             if have is not None:
                 have.close()

@@ -240,9 +240,7 @@ class GroupWrapper:
         debug_msg(f"tensor_devices={device_kinds}")
         debug_msg(f"{target_device=}")
         with debug_time("all_gather_placeholders"):
-            all_placeholders: List[List[TensorPlaceholder]] = self.all_gather_object(
-                [TensorPlaceholder(t) for t in my_tensors]
-            )
+            all_placeholders = self._gather_placeholders(my_tensors)
         self.last_snapshots = []
         if any(t.is_cuda for t in my_tensors):
             assert all(t.is_cuda for t in my_tensors), "all_gather_batch: mixed CPU/CUDA tensor lists are not supported"
@@ -268,6 +266,30 @@ class GroupWrapper:
                 views = [v.to(target_device, non_blocking=True) for v in views]
             result.append(views)
         return result
+
+    def all_gather_int(self, value: int) -> List[int]:
+        """All-gather one int64 per rank with a plain tensor collective (no pickling): used to agree on cache keys."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.backend != "gloo" and torch.cuda.is_available() else torch.device("cpu")
+        mine = torch.tensor([value], dtype=torch.int64, device=dev)
+        out = torch.empty(self.world_size, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.tolist()
+
+    def _gather_placeholders(self, my_tensors: List[torch.Tensor]) -> List[List[TensorPlaceholder]]:
+        """Shapes / dtypes of every member's tensor list.  The pickled exchange (reference ``:356-358``) is repeated only
+        when some member's structure changed: every call all-gathers one 64-bit fingerprint per rank, and the vector
+        of fingerprints -- identical on all members -- is the cache key."""
+        import hashlib
+
+        sig = repr([(tuple(t.shape), str(t.dtype), t.device.type, tuple(t.stride())) for t in my_tensors])
+        fingerprint = int.from_bytes(hashlib.blake2b(sig.encode(), digest_size=7).digest(), "little")
+        key = tuple(self.all_gather_int(fingerprint))
+        cache = self.__dict__.setdefault("_placeholder_cache", {})
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = self.all_gather_object([TensorPlaceholder(t) for t in my_tensors])
+        return cache[key]
 
     def isend_state_dict(self, state_dict: TensorAwareStateDict, dst: int) -> Dict[str, float]:
         """Send ``state_dict`` to global rank ``dst``: the hollow skeleton as an object, the payload as ONE

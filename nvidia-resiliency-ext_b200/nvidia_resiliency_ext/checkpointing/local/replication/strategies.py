@@ -59,7 +59,10 @@ class CliqueReplicationStrategy(ReplicationStrategy):
     def replicate(self, local_ckpt: TensorAwareStateDict, id_: str) -> Tuple[List[TensorAwareStateDict], List[str]]:
         payload = local_ckpt.pop_tensors()  # local_ckpt is hollow (and picklable) from here on
         with debug_time("all_gather_hollow_ckpt"):
-            skeletons = self.local_group.all_gather_object(local_ckpt)
+            # skeleton and id travel together (the reference gathers them in two rounds, ``:113`` and ``:135``)
+            gathered = self.local_group.all_gather_object((local_ckpt, id_))
+        skeletons = [g[0] for g in gathered]
+        ids = [g[1] for g in gathered]
         assert all(s.is_hollow for s in skeletons)
 
         with debug_time("all_gather_others_tensor_data"):
@@ -72,8 +75,6 @@ class CliqueReplicationStrategy(ReplicationStrategy):
             skeleton.insert_tensors(tensors)
         assert all(not s.is_hollow for s in skeletons)
 
-        with debug_time("all_gather_other_ids"):
-            ids = self.local_group.all_gather_object(id_)
         debug_msg(f"{sent_bytes=}")
         debug_msg(f"{recv_bytes=}")
         assert local_ckpt.is_hollow
