@@ -7,10 +7,10 @@ WHAT=${1:-all}
 
 # Memory guard: the box's cgroup (memory.max, 200 GiB on a 1-GPU box) also counts tmpfs / POSIX-shm pages, i.e. the
 # pinned snapshot slots and the checkpoint files in /dev/shm.  Exceeding it kills the whole box.  Every workload below
-# runs in its own session; a watcher kills that session (only it) and removes our shm files above 70 % of the limit.
+# runs in its own session; a watcher kills that session (only it) and removes our shm files above 80 % of the limit.
 MEM_MAX=$(cat /sys/fs/cgroup/memory.max 2>/dev/null || echo max)
 [[ $MEM_MAX == max ]] && MEM_MAX=$(( $(grep MemTotal /proc/meminfo | awk '{print $2}') * 1024 ))
-MEM_CAP=$(( MEM_MAX / 10 * 7 ))
+MEM_CAP=$(( MEM_MAX / 100 * ${MEM_GUARD_PCT:-80} ))
 guarded() {
   setsid "$@" &
   local pid=$!
