@@ -59,10 +59,15 @@ def _private_buffer(engine: SnapshotEngine, nbytes: int) -> DeviceBuffer:
 
 # ---- the clique-shared exchange buffer and its NVLink peer mappings -----------------------------------
 def _drop_peer_maps(engine: SnapshotEngine) -> None:
-    for pm in getattr(engine, "_peer_maps", {}).values():
+    maps = getattr(engine, "_peer_maps", None)
+    if maps is None:
+        engine._peer_maps = {}
+        return
+    for pm in maps.values():
         for ptr in pm["imported"]:
             engine.lib.nvrx_ipc_close(engine.device, ptr)
-    engine._peer_maps = {}
+    maps.clear()  # in place: callers hold a reference to this dict (re-binding it lost the new entries -> the next
+    #               regeneration re-imported handles that were still mapped: cudaErrorAlreadyMapped at 8 ranks)
 
 
 def _exchange_mode() -> str:

@@ -176,3 +176,30 @@ def test_parallel_gather_into_slot(built_library):
         hb.gather([srcs[3].data_ptr()], [3_000_000], [hb.capacity - 10], threads=2)  # would run past the slot
     del view
     hb.close()
+
+
+def test_persistent_writer_keeps_slots_mapped(built_library, tmp_path, monkeypatch):
+    """The persistent worker sets NVRX_B200_CACHE_SLOTS: the slot mapping is reused across checkpoints and stale ones
+    (slot re-created under another name) are dropped."""
+    from nvidia_resiliency_ext.checkpointing.b200 import persist
+    from nvidia_resiliency_ext.checkpointing.b200.persist import SnapshotRef, save_snapshot_with_torch
+
+    monkeypatch.setenv("NVRX_B200_CACHE_SLOTS", "1")
+    persist._slot_cache.clear()
+    name = f"/nvrx_test_c_{os.getpid()}"
+    hb, desc, a, b = _fake_snapshot(name)
+    skeleton = {"a": SnapshotRef(0), "b": SnapshotRef(1)}
+    for i in range(2):
+        save_snapshot_with_torch(skeleton, tmp_path / f"c{i}.pt", desc)
+        got = torch.load(tmp_path / f"c{i}.pt")
+        assert torch.equal(got["a"], a) and torch.equal(got["b"], b)
+    assert list(persist._slot_cache) == [name]
+    cached = persist._slot_cache[name]
+    hb.close()  # owner re-creates the slot under a new name
+    name2 = name + "_g2"
+    hb2, desc2, a2, b2 = _fake_snapshot(name2)
+    save_snapshot_with_torch(skeleton, tmp_path / "c2.pt", desc2)
+    assert list(persist._slot_cache) == [name2]  # the stale mapping was closed and dropped
+    assert torch.equal(torch.load(tmp_path / "c2.pt")["a"], a2)
+    persist._slot_cache.pop(name2).close(unlink=False)
+    hb2.close()
