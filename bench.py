@@ -195,7 +195,7 @@ def shm_dir(rank):
 # ----------------------------------------------------------------------------------------------------
 def run_engine(args, rank, world, local):
     from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
-    from nvidia_resiliency_ext.checkpointing.b200.engine import Event, Plan, SnapshotEngine
+    from nvidia_resiliency_ext.checkpointing.b200.engine import Event, SnapshotEngine
 
     dev = torch.device("cuda", local)
     sd, total = llama3_8b_shard_state(dev, seed=1234 + rank, scale=args.scale)

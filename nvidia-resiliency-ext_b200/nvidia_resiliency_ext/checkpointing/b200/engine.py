@@ -25,7 +25,7 @@ import os
 import threading
 import uuid
 from dataclasses import dataclass, field
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -276,9 +276,7 @@ class HostBuffer:
         if nbytes == 0:
             return torch.empty(0, dtype=torch.uint8)
         raw = (C.c_uint8 * nbytes).from_address(self.data_ptr)
-        t = torch.frombuffer(raw, dtype=torch.uint8)
-        t._nvrx_hostbuf = self  # keep this object (not the mapping!) alive with the base tensor
-        return t
+        return torch.frombuffer(raw, dtype=torch.uint8)
 
     def segment(self, offset: int, nbytes: int, dtype: torch.dtype, shape) -> torch.Tensor:
         """Typed CPU tensor over ``[offset, offset + nbytes)`` of the payload with a *storage of its own*.

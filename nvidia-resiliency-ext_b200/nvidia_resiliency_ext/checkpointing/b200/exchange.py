@@ -18,12 +18,11 @@ from __future__ import annotations
 import ctypes as C
 import os
 import socket
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
-from . import _cabi
 from ._cabi import check
 from .engine import DeviceBuffer, Event, PackedLayout, Snapshot, SnapshotEngine, dtype_name, expected_layout, host_views
 

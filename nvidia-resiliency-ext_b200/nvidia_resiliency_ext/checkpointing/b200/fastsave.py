@@ -17,7 +17,7 @@ import ctypes as C
 import os
 import pickle
 from contextlib import contextmanager
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 

@@ -28,7 +28,7 @@ import re
 from collections import defaultdict
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
-from typing import Dict, List, Optional, Sequence, Tuple, Union
+from typing import List, Optional, Tuple, Union
 
 import torch
 import torch.distributed as dist
@@ -39,7 +39,7 @@ from ...b200.persist import fast_zip_writes, wait_for_snapshots
 from ...utils import _disable_gc, debug_time
 from ..base_state_dict import TensorAwareStateDict
 from ..replication.group_utils import GroupWrapper, ProcessGroupLike, parse_group_sequence
-from .base_manager import CheckpointingException, CkptID
+from .base_manager import CheckpointingException
 from .local_manager import LocalCheckpointManager
 
 logger = logging.getLogger(__name__)
@@ -73,8 +73,6 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
         self.clique: GroupWrapper = GroupWrapper.wrap(clique)
         assert self.clique.world_size >= 2, "striped replication needs at least two clique members"
         self._members: List[int] = list(self.clique.ranks)
-        self._xbuf = None  # device exchange buffer (GPU path)
-        self._peer_key = None
 
     @classmethod
     def from_replication_params(cls, root_local_ckpt_dir, session_id: str = "", replication_jump: int = 1,

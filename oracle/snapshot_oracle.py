@@ -27,7 +27,6 @@ PINNING (how this oracle is tied to the real reference; see tests/golden/make_go
 
 from __future__ import annotations
 
-import os
 import random
 import time
 from collections import defaultdict

@@ -1,6 +1,5 @@
 """End-to-end probes on one GPU: sequential pack+drain vs the pipelined nvrx_snapshot, chunk sizes, 2-stream drain,
 host-side overhead of the API call.  Prints a table; run under gpurun."""
-import ctypes as C
 import os
 import sys
 import time
@@ -12,7 +11,7 @@ import torch  # noqa: E402
 
 from bench import flatten, llama3_8b_shard_state  # noqa: E402
 from nvidia_resiliency_ext.checkpointing.b200 import _cabi  # noqa: E402
-from nvidia_resiliency_ext.checkpointing.b200.engine import DeviceBuffer, Event, HostBuffer, Plan, SnapshotEngine, Stream  # noqa: E402
+from nvidia_resiliency_ext.checkpointing.b200.engine import DeviceBuffer, Event, HostBuffer, Plan, Stream  # noqa: E402
 
 def main():
     lib = _cabi.lib()
