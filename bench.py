@@ -108,7 +108,15 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+
+            def pump():
+                for ln in self.proc.stdout:
+                    self.lines.append(ln)
+
+            threading.Thread(target=pump, daemon=True).start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:  # nvidia-smi needs a moment (longer on 8-GPU boxes)
+                time.sleep(0.05)
         return self
 
     def __exit__(self, *exc):
@@ -207,17 +215,18 @@ def run_engine(args, rank, world, local):
     mask = SnapshotEngine._narrow_mask(tensors, args.narrow)
     plan = engine._plan_for(tensors, mask)
     staging = engine._ensure_staging(plan.staging_bytes)
+    clocks = ClockSampler(local)
+    clocks.__enter__()  # sampled from here until the end of the end-to-end loop (both timed regions)
     for _ in range(args.warmup):
         plan.pack(staging.ptr, stream)
     e0, e1 = Event(local, True), Event(local, True)
     torch.cuda.synchronize()
     dist.barrier()
-    with ClockSampler(local) as clocks:
-        e0.record(stream)
-        for _ in range(args.steps):
-            plan.pack(staging.ptr, stream)
-        e1.record(stream)
-        e1.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan.pack(staging.ptr, stream)
+    e1.record(stream)
+    e1.synchronize()
     kernel_ms = max_over_ranks(e0.elapsed_ms(e1) / args.steps)
     torch.cuda.synchronize()
     dist.barrier()
@@ -265,6 +274,7 @@ def run_engine(args, rank, world, local):
             stall.append(t1 - t0)
             host_safe.append(t2 - t0)
             persist.append(t3 - t0)
+    clocks.__exit__(None, None, None)
     launches += engine.launches - (engine_launches_before or 0)  # pack sub-launches of the pipelined snapshots
     e2e_s = max_over_ranks(median(host_safe))
     stall_ms = max_over_ranks(median(stall)) * 1e3
