@@ -113,6 +113,11 @@ int nvrx_scatter(nvrx_plan* plan, const void* staging, void* stream);
 int nvrx_pack_sharded(nvrx_plan* plan, void* staging, void* const* peer_bases, int n_peers, uint64_t shard_bytes,
                       uint64_t slot_offset, void* stream);
 
+/* Walk order of nvrx_pack_sharded: start with the tiles of shard `first_shard` and wrap around (default 0).  Members of
+ * a clique pass different values (rank r starts at the shard owned by r+1) so that at any moment they store into
+ * different destination GPUs instead of all into the same one. */
+int nvrx_plan_set_shard_rotation(nvrx_plan* plan, uint32_t first_shard);
+
 /* Fused pack + all-gather (reference-identical full replication, strategies.py:88-140): every packed byte is
  * written to ALL `n_peers` buffers at peer_bases[j] + slot_offset + position.  The source tensors are read from
  * HBM once; remote copies travel as NVLink P2P stores issued by the same kernel (TMA bulk stores from the one

@@ -62,8 +62,9 @@ struct nvrx_plan {
     uint64_t staging_bytes = 0;
     uint64_t algo_bytes = 0;
 
-    // sharding of the packed range for the fused exchange (0 = none)
+    // sharding of the packed range for the fused exchange (0 = none); the walk starts at shard `first_shard`
     uint64_t shard_bytes = 0;
+    uint32_t first_shard = 0;
 
     // descriptor tables.  The planner itself never touches CUDA (so its logic is testable without a GPU): host
     // vectors are authoritative, the pinned upload mirror and the device copy are created by the first upload.
@@ -126,6 +127,22 @@ int build_tiles(nvrx_plan* p) {
     }
     const size_t total = bulk.size() + ragged.size();
     if (total > 0xffffffffull) return NVRX_E_INVALID;
+    if (p->shard_bytes && p->first_shard) {
+        // Rotate both lists so the walk starts with the tiles of shard `first_shard` and wraps around.  CTAs take
+        // tiles in list order, so list order is time order: giving every rank a different starting shard keeps the
+        // ranks of a clique from storing into the same destination GPU at the same time (NVLink incast).
+        const uint64_t start = static_cast<uint64_t>(p->first_shard) * p->shard_bytes;
+        auto pos_of = [&](const TileDesc& t) {
+            const bool nr = (p->flags[t.seg] & NVRX_SEG_NARROW_F32_BF16) != 0;
+            return p->off[t.seg] + (nr ? t.off / 2 : t.off);
+        };
+        auto rot = [&](std::vector<TileDesc>& v) {
+            auto it = std::partition_point(v.begin(), v.end(), [&](const TileDesc& t) { return pos_of(t) < start; });
+            std::rotate(v.begin(), it, v.end());
+        };
+        rot(bulk);
+        rot(ragged);
+    }
     p->h_tiles.clear();
     p->h_tiles.reserve(total);
     p->h_tiles.insert(p->h_tiles.end(), bulk.begin(), bulk.end());
@@ -410,6 +427,15 @@ int nvrx_plan_update_ptrs(nvrx_plan* p, const void* const* ptrs) {
     return NVRX_OK;
 }
 
+int nvrx_plan_set_shard_rotation(nvrx_plan* p, uint32_t first_shard) {
+    if (!p) return NVRX_E_INVALID;
+    if (p->first_shard != first_shard) {
+        p->first_shard = first_shard;
+        if (p->shard_bytes) return build_tiles(p);
+    }
+    return NVRX_OK;
+}
+
 int nvrx_plan_tiles(const nvrx_plan* p, uint64_t shard_bytes, uint32_t* n_bulk, uint32_t* n_tiles, uint32_t* seg, uint32_t* nbytes,
                     uint64_t* off, uint64_t capacity) {
     if (!p) return NVRX_E_INVALID;
@@ -423,6 +449,7 @@ int nvrx_plan_tiles(const nvrx_plan* p, uint64_t shard_bytes, uint32_t* n_bulk, 
         tmp.off = p->off;
         tmp.flags = p->flags;
         tmp.shard_bytes = shard_bytes;
+        tmp.first_shard = p->first_shard;
         int rc = build_tiles(&tmp);
         if (rc) return rc;
         src = &tmp;

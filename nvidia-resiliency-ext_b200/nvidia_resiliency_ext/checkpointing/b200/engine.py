@@ -131,6 +131,9 @@ class Plan:
             "nvrx_pack_sharded",
         )
 
+    def set_shard_rotation(self, first_shard: int) -> None:
+        check(self._lib.nvrx_plan_set_shard_rotation(self._h, first_shard), "nvrx_plan_set_shard_rotation")
+
     def pack_broadcast(self, peer_bases: Sequence[int], slot_offset: int, stream: int) -> None:
         check(
             self._lib.nvrx_pack_broadcast(self._h, _ptr_array(peer_bases), len(peer_bases), slot_offset, stream),

@@ -325,6 +325,9 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
             dest = []
             for k, m in enumerate(self._others(me)):
                 dest.append(bases[self._members.index(m)] + self._slot_of_sender(me, m) * frag_slot)
+            # every member starts its walk at the fragment owned by its right-hand neighbour: distinct destinations
+            nxt = self._members[(self._members.index(me) + 1) % len(self._members)]
+            plan.set_shard_rotation(self._others(me).index(nxt))
             xch._clique_barrier(engine, self.clique)
             plan.pack_sharded(staging.ptr, dest, sb, 0, stream)
             engine.launches += 1 if plan.n_tiles else 0

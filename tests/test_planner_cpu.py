@@ -107,3 +107,24 @@ def test_planner_rejects_bad_arguments(built_library):
     with pytest.raises(SnapError):
         p.update_ptrs([0, 0])
     p.close()
+
+
+def test_shard_rotation_only_reorders(built_library):
+    """nvrx_plan_set_shard_rotation: same tiles, walk starts at the requested shard and wraps (per list)."""
+    nbytes = [3 << 20, 100, 5 << 20, 4, 1 << 20]
+    ptrs = [0x7F0000000000 + i * (16 << 20) for i in range(len(nbytes))]
+    plan = plan_for(ptrs, nbytes, tile_bytes=32768)
+    total = plan.staging_bytes
+    shard = orc.shard_bounds(total, 4, 512)[0]
+    nb0, base = plan.tiles(shard)
+    pos = lambda t: plan.offsets[t[0]] + t[2]  # noqa: E731
+    for first in (1, 2, 3):
+        plan.set_shard_rotation(first)
+        nb, tiles = plan.tiles(shard)
+        assert nb == nb0 and sorted(tiles) == sorted(base)
+        assert pos(tiles[0]) // shard == first                      # bulk list starts inside the requested shard
+        shards = [pos(t) // shard for t in tiles[:nb]]
+        assert shards == sorted(shards[: len(shards)], key=lambda s: (s - first) % 4)  # first, first+1, ..., wrap
+    plan.set_shard_rotation(0)
+    assert plan.tiles(shard)[1] == base
+    plan.close()
