@@ -493,6 +493,7 @@ class SnapshotEngine:
         self._staging_free: Optional[Event] = None  # recorded when the last reader of staging finished
         self._side = Stream(self.device)
         self._slots = [_Slot(i) for i in range(max(1, host_slots))]
+        self.max_host_slots = max(len(self._slots), int(os.environ.get("NVRX_B200_MAX_HOST_SLOTS", "4")))
         self._slot_gen = 0
         self.launches = 0  # kernels launched by this engine (pack + scatter)
         self._pid = os.getpid()  # forked writers inherit this object; only the creator may tear it down
@@ -533,12 +534,17 @@ class SnapshotEngine:
             # prefer a free slot that is already large enough (no re-pinning), then any free slot
             free = [s for s in self._slots if not s.busy]
             slot = next((s for s in free if s.buf is not None and s.buf.capacity >= nbytes), free[0] if free else None)
+        if slot is None and len(self._slots) < self.max_host_slots:
+            # every slot still belongs to an unfinalized save: grow the pool (the reference allocates fresh pinned
+            # memory for every save, too); bounded so a caller that never finalizes fails loudly instead of eating RAM
+            slot = _Slot(len(self._slots))
+            self._slots.append(slot)
         if slot is None:
             raise SnapError(
                 _cabi.E_STATE,
                 "acquiring a host snapshot slot",
                 f"all {len(self._slots)} slots hold unfinalized snapshots; finalize earlier saves first "
-                "(or raise host_slots)",
+                "(or raise NVRX_B200_MAX_HOST_SLOTS)",
             )
         if slot.buf is None or slot.buf.capacity < nbytes:
             if slot.buf is not None:
