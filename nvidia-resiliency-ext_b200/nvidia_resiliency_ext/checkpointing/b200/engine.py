@@ -715,6 +715,22 @@ class SnapshotEngine:
         plan.scatter(staging_ptr, self._current_stream())
         self.launches += 1 if plan.n_tiles else 0
 
+    def trim(self) -> None:
+        """Give memory back between checkpoints: the device staging buffer (as large as the snapshot) and every host slot
+        that is not owned by an unfinalized save.  The next snapshot re-creates what it needs (cudaMalloc + memset of the
+        staging buffer: milliseconds; pinning a 16 GB slot: ~2 s)."""
+        if self._staging is not None:
+            if self._staging_free is not None:
+                self._staging_free.synchronize()
+            self._staging.close()
+            self._staging = None
+        for s in self._slots:
+            if not s.busy and s.buf is not None:
+                if s.done_event is not None:
+                    s.done_event.synchronize()
+                s.buf.close()
+                s.buf = None
+
     def close(self) -> None:
         if os.getpid() != self._pid:
             return

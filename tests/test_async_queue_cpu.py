@@ -152,3 +152,24 @@ def test_debug_time_log_format(caplog):
     msgs = [r.getMessage() for r in caplog.records]
     assert any(m.startswith("outer.finalize_fn took ") and m.endswith("s") for m in msgs)
     assert any(m.startswith("outer took ") for m in msgs)
+
+
+def test_torch_async_checkpoint_with_host_state_dict(tmp_path, dist_1rank):
+    """BASELINE config C1 through TorchAsyncCheckpoint itself: a state dict without CUDA tensors needs no engine (and the
+    persistent worker must come up on a machine without a GPU -- the reference's worker divides by device_count() there)."""
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
+
+    g = torch.Generator().manual_seed(0)
+    sd = {f"p{i}": torch.randn(256, 64, generator=g) for i in range(8)}
+    sd["meta"] = {"step": 7, "ids": torch.arange(5)}
+    for persistent in (True, False):
+        ckpt = TorchAsyncCheckpoint(persistent_queue=persistent)
+        out = tmp_path / f"c1_{persistent}.pt"
+        ckpt.async_save(sd, out)
+        ckpt.save(sd, tmp_path / "sync.pt")
+        ckpt.finalize_async_save(blocking=True)
+        a, s = torch.load(out), torch.load(tmp_path / "sync.pt")
+        assert list(a) == list(s) and all(torch.equal(a[k], s[k]) for k in sd if k != "meta")
+        assert a["meta"]["step"] == 7 and torch.equal(a["meta"]["ids"], torch.arange(5))
+        assert ckpt._get_async_calls_queue().get_num_unfinalized_calls() == 0
+        ckpt.close()
