@@ -198,6 +198,12 @@ class Stream:
             self._lib.nvrx_stream_destroy(self.handle)
             self.handle = 0
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class Event:
     def __init__(self, device: int, timing: bool = False):
@@ -226,6 +232,12 @@ class Event:
         if self.handle:
             self._lib.nvrx_event_destroy(self.handle)
             self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def stream_wait_event(stream: int, ev: Event) -> None:
