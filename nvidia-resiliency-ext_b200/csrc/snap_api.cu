@@ -345,6 +345,7 @@ int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes,
     }
     nvrx_plan* p = new (std::nothrow) nvrx_plan();
     if (!p) return NVRX_E_NOMEM;
+    try {  // the ABI never throws: container growth failures become NVRX_E_NOMEM
     p->device = device;
     p->n = n;
     p->align = align;
@@ -375,6 +376,10 @@ int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes,
     if (rc) {
         nvrx_plan_destroy(p);
         return rc;
+    }
+    } catch (const std::bad_alloc&) {
+        nvrx_plan_destroy(p);
+        return NVRX_E_NOMEM;
     }
     *out = p;
     return NVRX_OK;
@@ -422,8 +427,12 @@ int nvrx_plan_update_ptrs(nvrx_plan* p, const void* const* ptrs) {
         if (((np ^ p->ptrs[i]) & 15u) != 0) same_class = false;
     }
     for (int64_t i = 0; i < p->n; ++i) p->ptrs[i] = reinterpret_cast<uint64_t>(ptrs[i]);
-    fill_segs(p);
-    if (!same_class) return build_tiles(p);
+    try {
+        fill_segs(p);
+        if (!same_class) return build_tiles(p);
+    } catch (const std::bad_alloc&) {
+        return NVRX_E_NOMEM;
+    }
     return NVRX_OK;
 }
 
