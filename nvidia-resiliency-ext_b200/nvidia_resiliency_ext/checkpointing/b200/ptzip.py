@@ -1,0 +1,280 @@
+"""A ``torch.load``-able checkpoint container whose tensor payload sits at offsets WE choose.
+
+PyTorch checkpoints are ZIP archives of *stored* (uncompressed) records; ``torch.load`` finds records through the central
+directory, so the order of records in the file is free.  ``torch.save`` puts ``data.pkl`` first, which makes every payload
+offset depend on the size of the pickle.  This writer inverts that:
+
+    [ local header | data/0 ] [ local header | data/1 ] ...      <- payload region: offsets depend only on tensor sizes
+    [ data.pkl ] [ byteorder ] [ version ] ...                   <- small records, whatever PyTorch would have written
+    [ pad record ] [ central directory ] [ zip64 EOCD ] [ EOCD ] <- the tail can be pinned to the end of a fixed-size file
+
+so the payload region of the *file* can have the same geometry as the packed staging buffer of the snapshot engine.  It is
+the host half of zero-copy persistence (DESIGN.md "next"): the pinned host slot a snapshot drains into can be the tmpfs
+checkpoint file itself.  This module is CPU-only and self-contained; today it is exercised by ``tests/test_ptzip_cpu.py``
+and not yet on the default save path (that needs the file-backed slot to be validated on a GPU box).
+
+Small records (pickle with PyTorch's persistent-id scheme, ``version``, ``byteorder``, ...) are produced by PyTorch itself:
+``torch.save`` with ``skip_data`` into memory, read back record by record -- nothing about their content is hard-coded here.
+"""
+
+from __future__ import annotations
+
+import io
+import os
+import pickle
+import struct
+import zlib
+from dataclasses import dataclass, field
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+ALIGN = 64  # PyTorch aligns record data to 64 bytes (mmap-friendly)
+_PAD_ID = 0x4246  # "FB": the extra-field id PyTorch uses for its alignment padding
+_U32 = 0xFFFFFFFF
+
+
+@dataclass
+class Record:
+    name: str  # full name inside the archive ("<archive>/data/0")
+    size: int
+    header_off: int = 0
+    data_off: int = 0
+    crc: int = 0
+
+
+@dataclass
+class PayloadLayout:
+    """Where every storage record lives; a function of (archive name, storage sizes) only."""
+
+    archive: str
+    records: List[Record] = field(default_factory=list)
+    end: int = 0  # first byte after the last payload record
+
+
+def _local_header(name: bytes, size: int, crc: int, data_off_hint: int, header_off: int, force_zip64: bool) -> bytes:
+    """Local file header whose extra field pads the record data to ``ALIGN`` (and carries zip64 sizes when needed)."""
+    zip64 = force_zip64 or size >= _U32
+    extra = b""
+    if zip64:
+        extra += struct.pack("<HHQQ", 0x0001, 16, size, size)
+    fixed = 30 + len(name)
+    pad_to = data_off_hint - header_off - fixed - len(extra)
+    assert pad_to >= 4 or pad_to == 0, pad_to
+    if pad_to:
+        extra += struct.pack("<HH", _PAD_ID, pad_to - 4) + b"Z" * (pad_to - 4)
+    hdr = struct.pack(
+        "<IHHHHHIIIHH", 0x04034B50, 45 if zip64 else 20, 0, 0, 0, 0x21, crc & _U32,
+        _U32 if zip64 else size, _U32 if zip64 else size, len(name), len(extra),
+    )
+    return hdr + name + extra
+
+
+def _data_offset_after(header_off: int, name_len: int, zip64: bool) -> int:
+    """Smallest ALIGN-aligned data offset that leaves room for the header (+ zip64 extra) and a legal padding field."""
+    need = header_off + 30 + name_len + (20 if zip64 else 0)
+    off = -(-need // ALIGN) * ALIGN
+    while 0 < off - need < 4:  # a padding extra field needs at least its 4-byte header
+        off += ALIGN
+    return off
+
+
+def plan_payload(archive: str, sizes: Sequence[int], *, start: int = 0, force_zip64: bool = False) -> PayloadLayout:
+    """Lay out ``data/<i>`` records of the given sizes starting at file offset ``start``."""
+    lay = PayloadLayout(archive=archive)
+    cur = start
+    for i, size in enumerate(sizes):
+        name = f"{archive}/data/{i}"
+        zip64 = force_zip64 or size >= _U32
+        data_off = _data_offset_after(cur, len(name.encode()), zip64)
+        lay.records.append(Record(name=name, size=size, header_off=cur, data_off=data_off))
+        cur = data_off + size
+    lay.end = cur
+    return lay
+
+
+class _Recorder:
+    """Dry-run stand-in for PyTorchFileWriter: which storage became which ``data/<key>`` record."""
+
+    def __init__(self):
+        self.storages: List[Tuple[str, int, int]] = []
+
+    def write_record(self, name, data, nbytes):
+        if name.startswith("data/") and not isinstance(data, (str, bytes)):
+            self.storages.append((name, data.data_ptr(), int(nbytes)))
+
+    def write_record_metadata(self, name, nbytes):  # pragma: no cover
+        self.storages.append((name, 0, int(nbytes)))
+
+
+def describe(obj: Any, protocol: int = torch.serialization.DEFAULT_PROTOCOL) -> Tuple[List[Tuple[str, bytes]], List[Tuple[int, int]]]:
+    """``(small_records, storages)`` of ``obj`` as PyTorch would serialise it.
+
+    small_records: ``[(record name without archive prefix, bytes)]`` for everything that is not tensor data, in PyTorch's
+    order; storages: ``[(data_ptr, nbytes)]`` in key order (``data/0``, ``data/1``, ...)."""
+    rec = _Recorder()
+    torch.serialization._save(obj, rec, pickle, protocol, False)
+    keys = [int(n.split("/", 1)[1]) for n, _, _ in rec.storages]
+    assert keys == list(range(len(keys))), "storage keys are expected to be 0..n-1 in order"
+    buf = io.BytesIO()
+    with torch.serialization.skip_data():
+        torch.save(obj, buf, pickle_protocol=protocol)
+    buf.seek(0)
+    reader = torch._C.PyTorchFileReader(buf)
+    small = [(n, bytes(reader.get_record(n))) for n in reader.get_all_records() if not n.startswith("data/")]
+    return small, [(ptr, nb) for _, ptr, nb in rec.storages]
+
+
+def _central_entry(name: bytes, size: int, crc: int, header_off: int, force_zip64: bool) -> bytes:
+    z_size = force_zip64 or size >= _U32
+    z_off = force_zip64 or header_off >= _U32
+    extra = b""
+    if z_size or z_off:
+        body = b""
+        if z_size:
+            body += struct.pack("<QQ", size, size)
+        if z_off:
+            body += struct.pack("<Q", header_off)
+        extra = struct.pack("<HH", 0x0001, len(body)) + body
+    need = 45 if (z_size or z_off) else 20
+    return struct.pack(
+        "<IHHHHHHIIIHHHHHII", 0x02014B50, need, need, 0, 0, 0, 0x21, crc & _U32,
+        _U32 if z_size else size, _U32 if z_size else size, len(name), len(extra), 0, 0, 0, 0,
+        _U32 if z_off else header_off,
+    ) + name + extra
+
+
+_PAD_CRC_LIMIT = 256 << 20
+
+
+def _crc_of_file_range(fd: int, off: int, n: int) -> int:
+    crc, step = 0, 8 << 20
+    while n > 0:
+        chunk = os.pread(fd, min(step, n), off)
+        if not chunk:  # beyond EOF of a sparse file: zeros
+            chunk = bytes(min(step, n))
+        crc = zlib.crc32(chunk, crc)
+        off += len(chunk)
+        n -= len(chunk)
+    return crc & _U32
+
+
+def tail_size(archive: str, small: Sequence[Tuple[str, bytes]], n_storages: int, force_zip64: bool = False) -> int:
+    """Upper bound of the bytes needed after the payload region (small records + pad record + directory + EOCDs)."""
+    names = [f"{archive}/{n}" for n, _ in small] + [f"{archive}/data/{i}" for i in range(n_storages)] + [f"{archive}/.pad"]
+    local = sum(30 + len(n.encode()) + 20 + ALIGN + 4 for n in names[: len(small)] + names[-1:]) + sum(len(b) for _, b in small)
+    central = sum(46 + len(n.encode()) + 28 for n in names)
+    return local + central + 56 + 20 + 22 + 2 * ALIGN
+
+
+def write_container(
+    fd: int,
+    layout: PayloadLayout,
+    small: Sequence[Tuple[str, bytes]],
+    *,
+    file_size: Optional[int] = None,
+    crcs: Optional[Sequence[int]] = None,
+    write_payload: Optional[Callable[[Record], None]] = None,
+    force_zip64: bool = False,
+) -> int:
+    """Write headers, small records, pad record, central directory and EOCDs around a payload region planned by
+    :func:`plan_payload`.  Payload bytes themselves are NOT written unless ``write_payload(record)`` is given (they may
+    already be there: the region can be the destination of a DMA).
+
+    ``file_size``: when set, the archive is made to end exactly there (a ``.pad`` record absorbs the slack), so a fixed-size
+    pre-pinned file can be reused for snapshots of any smaller size.  Returns the archive end offset.
+    ``crcs[i]``: crc32 of storage i (0 when omitted -- ``torch.load`` does not verify; ``zipfile.testzip`` would)."""
+    archive = layout.archive
+    central: List[bytes] = []
+    # payload records: headers only
+    for i, rec in enumerate(layout.records):
+        rec.crc = (crcs[i] if crcs is not None else 0) & _U32
+        name = rec.name.encode()
+        os.pwrite(fd, _local_header(name, rec.size, rec.crc, rec.data_off, rec.header_off, force_zip64), rec.header_off)
+        if write_payload is not None and rec.size:
+            write_payload(rec)
+        central.append(_central_entry(name, rec.size, rec.crc, rec.header_off, force_zip64))
+    cur = layout.end
+    # small records (PyTorch's own bytes)
+    for n, data in small:
+        name = f"{archive}/{n}".encode()
+        crc = zlib.crc32(data) & _U32
+        data_off = _data_offset_after(cur, len(name), force_zip64)
+        os.pwrite(fd, _local_header(name, len(data), crc, data_off, cur, force_zip64), cur)
+        os.pwrite(fd, data, data_off)
+        central.append(_central_entry(name, len(data), crc, cur, force_zip64))
+        cur = data_off + len(data)
+    n_entries = len(central)
+    cd_bytes = b"".join(central)
+    tail_fixed = 56 + 20 + 22
+    if file_size is not None:
+        # a ".pad" record soaks up the slack so that the EOCD is the last thing in the file
+        name = f"{archive}/.pad".encode()
+        pad_central_len = 46 + len(name) + 28
+        data_off = _data_offset_after(cur, len(name), True)
+        slack = file_size - data_off - (len(cd_bytes) + pad_central_len + tail_fixed)
+        if slack < 0:
+            raise ValueError(f"file_size {file_size} too small for the container (short by {-slack} bytes)")
+        pad_entry = _central_entry(name, slack, 0, cur, True)
+        # the central entry was budgeted with the largest zip64 extra; make up the difference with a longer pad
+        slack += pad_central_len - len(pad_entry)
+        # the pad covers whatever the file holds there (zeros in a fresh file, stale bytes in a reused slot); its crc is
+        # only computed when that is cheap -- nothing ever reads the record, it exists to keep the EOCD at the file end
+        pad_crc = _crc_of_file_range(fd, data_off, slack) if slack <= _PAD_CRC_LIMIT else 0
+        pad_entry = _central_entry(name, slack, pad_crc, cur, True)
+        os.pwrite(fd, _local_header(name, slack, pad_crc, data_off, cur, True), cur)
+        cd_bytes += pad_entry
+        n_entries += 1
+        cur = data_off + slack
+    cd_off = cur
+    os.pwrite(fd, cd_bytes, cd_off)
+    cur = cd_off + len(cd_bytes)
+    # zip64 end of central directory + locator (always written: payloads are routinely > 4 GiB), then the classic EOCD
+    z64 = struct.pack("<IQHHIIQQQQ", 0x06064B50, 44, 45, 45, 0, 0, n_entries, n_entries, len(cd_bytes), cd_off)
+    loc = struct.pack("<IIQI", 0x07064B50, 0, cur, 1)
+    eocd = struct.pack(
+        "<IHHHHIIH", 0x06054B50, 0, 0, min(n_entries, 0xFFFF), min(n_entries, 0xFFFF),
+        min(len(cd_bytes), _U32), min(cd_off, _U32), 0,
+    )
+    os.pwrite(fd, z64 + loc + eocd, cur)
+    end = cur + len(z64) + len(loc) + len(eocd)
+    if file_size is not None:
+        assert end == file_size, (end, file_size)
+    return end
+
+
+def save(obj: Any, path, *, locate: Callable[[int, int], Optional[Tuple[Any, int]]], threads: int = 16,
+         compute_crc: bool = True, file_size: Optional[int] = None, force_zip64: bool = False) -> PayloadLayout:
+    """Write ``obj`` as a checkpoint with the payload-first layout.  ``locate(data_ptr, nbytes)`` maps a storage to
+    ``(HostBuffer, offset)`` (payload copied by the buffer's parallel writer) or ``None`` (copied from process memory)."""
+    import ctypes as C
+
+    small, storages = describe(obj)
+    archive = os.path.splitext(os.path.basename(os.fspath(path)))[0] or "archive"
+    layout = plan_payload(archive, [nb for _, nb in storages], force_zip64=force_zip64)
+    fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o644)
+    try:
+        total = file_size if file_size is not None else layout.end + tail_size(archive, small, len(storages), force_zip64)
+        os.ftruncate(fd, total)
+        crcs, by_buf = [], {}
+        for rec, (ptr, nb) in zip(layout.records, storages):
+            hit = locate(ptr, nb) if nb else None
+            if hit is None:
+                raw = C.string_at(ptr, nb) if nb else b""
+                os.pwrite(fd, raw, rec.data_off)
+                crcs.append(zlib.crc32(raw) if compute_crc else 0)
+            else:
+                hb, off = hit
+                ent = by_buf.setdefault(id(hb), (hb, [], [], []))
+                ent[1].append(off)
+                ent[2].append(nb)
+                ent[3].append(rec.data_off)
+                crcs.append(hb.crc32(off, nb, threads) if compute_crc else 0)
+        for hb, offs, sizes, file_offs in by_buf.values():
+            hb.writev_fd(offs, sizes, file_offs, fd, threads)
+        end = write_container(fd, layout, small, file_size=file_size, crcs=crcs, force_zip64=force_zip64)
+        if file_size is None:
+            os.ftruncate(fd, end)
+    finally:
+        os.close(fd)
+    return layout
