@@ -76,6 +76,10 @@ int nvrx_device_info(int device, int* sm_count, uint64_t* l2_bytes, char* name, 
  */
 int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes, const uint32_t* flags,
                      uint64_t align, uint32_t tile_bytes, int device, nvrx_plan** out);
+/* Same, with caller-chosen staging offsets (16-byte aligned, ascending, non-overlapping) instead of the round_up rule:
+ * lets the packed image coincide with the payload region of a checkpoint container (zero-copy persistence). */
+int nvrx_plan_create_at(int64_t n, const void* const* ptrs, const uint64_t* nbytes, const uint32_t* flags,
+                        const uint64_t* staging_offsets, uint64_t align, uint32_t tile_bytes, int device, nvrx_plan** out);
 int nvrx_plan_destroy(nvrx_plan* plan);
 /* total staging bytes / number of tiles (bulk + ragged) / algorithmic HBM bytes of one pack launch
  * (source bytes read + packed bytes written; SURVEY.md 8(d): 2*S, or 1.5*S_in with narrowing). */

@@ -331,7 +331,21 @@ int nvrx_device_info(int device, int* sm_count, uint64_t* l2_bytes, char* name, 
 
 int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes, const uint32_t* flags, uint64_t align,
                      uint32_t tile_bytes, int device, nvrx_plan** out) {
+    return nvrx_plan_create_at(n, ptrs, nbytes, flags, nullptr, align, tile_bytes, device, out);
+}
+
+int nvrx_plan_create_at(int64_t n, const void* const* ptrs, const uint64_t* nbytes, const uint32_t* flags,
+                        const uint64_t* staging_offsets, uint64_t align, uint32_t tile_bytes, int device, nvrx_plan** out) {
     if (!out || n < 0 || (n > 0 && (!ptrs || !nbytes))) return NVRX_E_INVALID;
+    if (staging_offsets) {
+        // caller-chosen layout (e.g. the record offsets of a checkpoint container): 16-byte aligned, ascending, disjoint
+        uint64_t prev_end = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const bool nr = flags && (flags[i] & NVRX_SEG_NARROW_F32_BF16);
+            if ((staging_offsets[i] & 15u) || staging_offsets[i] < prev_end) return NVRX_E_INVALID;
+            prev_end = staging_offsets[i] + (nr ? nbytes[i] / 2 : nbytes[i]);
+        }
+    }
     if (align == 0) align = kDefaultAlign;
     if (tile_bytes == 0) tile_bytes = kDefaultTile;
     if (!is_pow2(align) || align < 16) return NVRX_E_INVALID;
@@ -362,7 +376,7 @@ int nvrx_plan_create(int64_t n, const void* const* ptrs, const uint64_t* nbytes,
         const bool narrow = (p->flags[i] & NVRX_SEG_NARROW_F32_BF16) != 0;
         p->any_narrow |= narrow;
         p->packed[i] = narrow ? p->nbytes[i] / 2 : p->nbytes[i];
-        cur = round_up(cur, align);
+        cur = staging_offsets ? staging_offsets[i] : round_up(cur, align);
         p->off[i] = cur;
         cur += p->packed[i];
         src_total += p->nbytes[i];

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "nvrx_strerror",
     "nvrx_device_info",
     "nvrx_plan_create",
+    "nvrx_plan_create_at",
     "nvrx_plan_destroy",
     "nvrx_plan_info",
     "nvrx_plan_layout",
@@ -113,6 +114,7 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_strerror": (C.c_char_p, [_int]),
         "nvrx_device_info": (_int, [_int, P(_int), P(_u64), C.c_char_p, _int]),
         "nvrx_plan_create": (_int, [_i64, P(_vp), P(_u64), P(_u32), _u64, _u32, _int, P(_vp)]),
+        "nvrx_plan_create_at": (_int, [_i64, P(_vp), P(_u64), P(_u32), P(_u64), _u64, _u32, _int, P(_vp)]),
         "nvrx_plan_destroy": (_int, [_vp]),
         "nvrx_plan_info": (_int, [_vp, P(_u64), P(_u64), P(_u64)]),
         "nvrx_plan_layout": (_int, [_vp, P(_u64), P(_u64)]),

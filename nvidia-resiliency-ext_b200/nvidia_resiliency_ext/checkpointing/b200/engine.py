@@ -64,6 +64,7 @@ class Plan:
         align: int = 0,
         tile_bytes: int = 0,
         variant: int = _cabi.VARIANT_AUTO,
+        staging_offsets: Optional[Sequence[int]] = None,
     ):
         assert len(ptrs) == len(nbytes)
         self._lib = _cabi.lib()
@@ -71,11 +72,12 @@ class Plan:
         self.device = device
         self._h = C.c_void_p()
         flags_arr = _u32_array(flags) if flags is not None else None
+        offs_arr = _u64_array(staging_offsets) if staging_offsets is not None else None
         check(
-            self._lib.nvrx_plan_create(
-                self.n, _ptr_array(ptrs), _u64_array(nbytes), flags_arr, align, tile_bytes, device, C.byref(self._h)
+            self._lib.nvrx_plan_create_at(
+                self.n, _ptr_array(ptrs), _u64_array(nbytes), flags_arr, offs_arr, align, tile_bytes, device, C.byref(self._h)
             ),
-            "nvrx_plan_create",
+            "nvrx_plan_create_at",
         )
         stg, tiles, algo = C.c_uint64(), C.c_uint64(), C.c_uint64()
         check(self._lib.nvrx_plan_info(self._h, C.byref(stg), C.byref(tiles), C.byref(algo)), "nvrx_plan_info")

@@ -128,3 +128,23 @@ def test_shard_rotation_only_reorders(built_library):
     plan.set_shard_rotation(0)
     assert plan.tiles(shard)[1] == base
     plan.close()
+
+
+def test_explicit_staging_offsets_follow_a_checkpoint_container(built_library):
+    """nvrx_plan_create_at: the packed image can take the geometry of a payload-first container (b200/ptzip.py)."""
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+    from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
+
+    nbytes = [4 << 20, 4, 100_000, 0, 1 << 20]
+    ptrs = [(0x7F0000000000 + i * (16 << 20)) if nb else 0 for i, nb in enumerate(nbytes)]
+    lay = ptzip.plan_payload("ckpt", nbytes)
+    offs = [r.data_off for r in lay.records]
+    plan = plan_for(ptrs, nbytes, staging_offsets=offs)
+    assert list(plan.offsets) == offs and list(plan.packed_nbytes) == nbytes
+    assert plan.staging_bytes >= lay.end and plan.staging_bytes % 512 == 0
+    check_cover(plan, ptrs, nbytes, None, 32768)
+    plan.close()
+    with pytest.raises(SnapError):
+        plan_for(ptrs, nbytes, staging_offsets=[o + 8 for o in offs])      # not 16-byte aligned
+    with pytest.raises(SnapError):
+        plan_for(ptrs, nbytes, staging_offsets=[0, 64, 128, 256, 512])     # overlapping
