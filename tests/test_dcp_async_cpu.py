@@ -1,0 +1,230 @@
+"""torch.distributed.checkpoint through FileSystemWriterAsync, CPU only (gloo): the files must be byte-identical to a
+synchronous ``dcp.save`` of the same state dict, and ``dcp.load`` must give the values back.  Mirrors the scenarios of the
+reference's tests/checkpointing/unit/test_async_writer.py (sync-vs-async equality, cached-plan reuse, failure propagation)."""
+import filecmp
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.distributed.checkpoint as dcp
+from torch.distributed.checkpoint import CheckpointException, DefaultSavePlanner, FileSystemReader, FileSystemWriter
+
+from _mp import run_ranks
+
+
+def _state(rank=0, step=0):
+    g = torch.Generator().manual_seed(100 + rank)
+    return {
+        "model": {
+            "w": torch.randn(33, 17, generator=g) + step,
+            "b": torch.arange(7, dtype=torch.int64) * (rank + 1),
+            "h": torch.randn(5, 3, generator=g).to(torch.bfloat16),
+            "empty": torch.empty(0, 4),
+        },
+        "opt": {"step": torch.tensor(3 + step), "lr": 0.125, "name": f"adam{rank}"},
+    }
+
+
+def _async_save(state, path, queue, planner=None, **kw):
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncRequest
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import (
+        save_state_dict_async_finalize,
+        save_state_dict_async_plan,
+    )
+
+    writer = FileSystemWriterAsync(path, thread_count=2)
+    ret = save_state_dict_async_plan(state, writer, None, 0, planner=planner or DefaultSavePlanner(), **kw)
+    save_fn, preload_fn, save_args = writer.get_save_function_and_args()
+    assert save_fn is not None and getattr(save_fn, "nvrx_drain_aware", False)
+    req = AsyncRequest(save_fn, save_args, [lambda: save_state_dict_async_finalize(*ret)], preload_fn=preload_fn)
+    queue.schedule_async_request(req)
+    return ret
+
+
+def _same_files(a, b):
+    cmp = filecmp.dircmp(a, b)
+    assert not cmp.left_only and not cmp.right_only, (cmp.left_only, cmp.right_only)
+    data = [f for f in cmp.common_files if f.endswith(".distcp")]
+    assert data
+    match, mismatch, errors = filecmp.cmpfiles(a, b, data, shallow=False)
+    assert not mismatch and not errors, (mismatch, errors)
+
+
+def _loaded_equals(path, expect):
+    got = {k: ({kk: (torch.zeros_like(vv) if isinstance(vv, torch.Tensor) else None) for kk, vv in v.items()}) for k, v in expect.items()}
+    dcp.load(got, storage_reader=FileSystemReader(path))
+    for k, sub in expect.items():
+        for kk, vv in sub.items():
+            if isinstance(vv, torch.Tensor):
+                assert got[k][kk].dtype == vv.dtype and torch.equal(got[k][kk], vv), (k, kk)
+            else:
+                assert got[k][kk] == vv, (k, kk)
+
+
+@pytest.mark.parametrize("persistent", [False, True])
+def test_async_dcp_matches_sync_save(tmp_path, dist_1rank, persistent):
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+
+    state = _state()
+    sync_dir, async_dir = tmp_path / "sync", tmp_path / "async"
+    dcp.save(state, storage_writer=FileSystemWriter(sync_dir, thread_count=2), planner=DefaultSavePlanner())
+    q = AsyncCallsQueue(persistent=persistent)
+    try:
+        _async_save(state, async_dir, q)
+        # the trainer may change its tensors as soon as the request is scheduled
+        state["model"]["w"].add_(1000.0)
+        state["model"]["b"].zero_()
+        q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+        assert q.get_num_unfinalized_calls() == 0
+    finally:
+        q.close()
+    _same_files(sync_dir, async_dir)
+    _loaded_equals(async_dir, _state())
+
+
+def _two_rank_job(rank, world, root):
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import (
+        CheckpointMetadataCache,
+        get_metadata_caching_status,
+    )
+
+    q = AsyncCallsQueue(persistent=False)
+    cache = CheckpointMetadataCache()
+    for step in range(3):
+        state = {f"r{rank}": _state(rank, step)["model"], "shared": {"s": torch.full((4,), float(step))}}
+        sync_dir, async_dir = os.path.join(root, f"sync{step}"), os.path.join(root, f"async{step}")
+        dcp.save(state, storage_writer=FileSystemWriter(sync_dir, thread_count=2), planner=DefaultSavePlanner())
+        ret = _async_save(state, async_dir, q, enable_cache=True, metadata_cache=cache)
+        # plans are identical from the second save on: the third one must have skipped the exchange
+        assert cache.validated_cache_reuse == (step >= 1), (step, cache.get_metadata_caching_status())
+        assert (ret[1] is not None) == (rank == 0)
+        q.maybe_finalize_async_calls(blocking=True)
+        dist.barrier()
+        if rank == 0:
+            _same_files(sync_dir, async_dir)
+            assert {f[:4] for f in os.listdir(async_dir) if f.endswith(".distcp")} == {"__0_", "__1_"}
+        got = {f"r{rank}": {k: torch.zeros_like(v) for k, v in state[f"r{rank}"].items()}, "shared": {"s": torch.zeros(4)}}
+        dcp.load(got, storage_reader=FileSystemReader(async_dir))
+        for k, v in state[f"r{rank}"].items():
+            assert torch.equal(got[f"r{rank}"][k], v), (step, k)
+        assert torch.equal(got["shared"]["s"], state["shared"]["s"])
+    assert get_metadata_caching_status() is None  # the process-wide cache was never created
+    q.close()
+
+
+def test_async_dcp_two_ranks_with_plan_cache(tmp_path):
+    run_ranks(_two_rank_job, 2, str(tmp_path))
+
+
+def _failing_job(rank, world, root):
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+
+    q = AsyncCallsQueue(persistent=False)
+    target = os.path.join(root, "ckpt")
+    state = {f"r{rank}": {"w": torch.ones(8) * rank}}
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import (
+        save_state_dict_async_finalize,
+        save_state_dict_async_plan,
+    )
+
+    writer = FileSystemWriterAsync(target, thread_count=1)
+    ret = save_state_dict_async_plan(state, writer, None, 0)
+    save_fn, preload_fn, save_args = writer.get_save_function_and_args()
+    if rank == 1:
+        # rank 1's writer process cannot create its file: the directory is replaced by a plain file
+        dist.barrier()
+        import shutil
+
+        shutil.rmtree(target)
+        open(target, "w").close()
+        dist.barrier()
+    else:
+        dist.barrier()
+        dist.barrier()
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncRequest
+
+    q.schedule_async_request(AsyncRequest(save_fn, save_args, [], preload_fn=preload_fn))
+    q.maybe_finalize_async_calls(blocking=True)
+    with pytest.raises(CheckpointException) as err:
+        save_state_dict_async_finalize(*ret)
+    if rank == 0:
+        assert set(err.value.failures) == {0, 1} or 1 in err.value.failures
+    assert not os.path.exists(os.path.join(target, ".metadata"))
+    q.close()
+
+
+def test_async_dcp_write_failure_raises_everywhere(tmp_path):
+    run_ranks(_failing_job, 2, str(tmp_path))
+
+
+def test_writer_process_reads_cuda_items_from_the_snapshot_slot(tmp_path, built_library):
+    """Writer side of the engine path without a GPU: the slot content is produced by the oracle's pack, the progress word
+    is advanced by a thread (as the side stream would), and the write function must wait for it and write the same file
+    as a synchronous save of the tensors."""
+    import ctypes as C
+    import multiprocessing
+    import threading
+    import time
+
+    from oracle.snapshot_oracle import pack_oracle
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import save_state_dict_async_plan
+    from nvidia_resiliency_ext.checkpointing.b200.engine import HostBuffer, PackedLayout
+
+    state = _state()
+    sync_dir, async_dir = tmp_path / "sync", tmp_path / "async"
+    dcp.save(state, storage_writer=FileSystemWriter(sync_dir, thread_count=1), planner=DefaultSavePlanner())
+
+    writer = FileSystemWriterAsync(async_dir, thread_count=1)
+    _, metadata, dist_wrapper = save_state_dict_async_plan(state, writer, None, 0)
+    payload = writer._payload
+    # pretend every tensor item was on the GPU: move it from the host staging into a packed slot
+    tensor_idx = [i for i, v in payload["host"].items() if isinstance(v, torch.Tensor)]
+    tensors = [payload["host"].pop(i) for i in tensor_idx]
+    packed, offs, sizes = pack_oracle(tensors)
+    names = {torch.float32: "float32", torch.int64: "int64", torch.bfloat16: "bfloat16"}
+    layout = PackedLayout(
+        shapes=[tuple(t.shape) for t in tensors], dtypes=[names[t.dtype] for t in tensors],
+        src_dtypes=[names[t.dtype] for t in tensors], offsets=list(offs), packed_nbytes=list(sizes), total_bytes=len(packed),
+    )
+    hb = HostBuffer.create(max(len(packed), 4096), name=f"/nvrx_dcp_{os.getpid()}", pin=False, prefault_threads=1)
+    try:
+        payload["snapshot"] = {"shm_name": hb.name, "progress_target": 7, "layout": layout}
+        payload["cuda_indices"] = tensor_idx
+
+        def drain():
+            time.sleep(0.2)
+            hb.as_tensor(len(packed)).numpy()[:] = packed
+            C.c_uint64.from_address(hb.progress_ptr).value = 7
+
+        t = threading.Thread(target=drain)
+        t.start()
+        results = multiprocessing.get_context("spawn").Manager().Queue()
+        FileSystemWriterAsync.write_preloaded_data(writer._ctor, 1, 0, payload, results)
+        t.join()
+        rank, outcome = results.get(timeout=10)
+        assert rank == 0 and isinstance(outcome, list) and len(outcome) == len(payload["plan"].items), outcome
+        writer.finish(metadata, [outcome])
+    finally:
+        hb.close()
+    _same_files(sync_dir, async_dir)
+    _loaded_equals(async_dir, _state())
+
+
+def test_writer_rejects_unsupported_modes(tmp_path):
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+
+    with pytest.raises(NotImplementedError):
+        FileSystemWriterAsync(tmp_path, single_file_per_rank=False)
+    with pytest.raises(NotImplementedError):
+        FileSystemWriterAsync(tmp_path, use_msc=True)
+    w = FileSystemWriterAsync(tmp_path)
+    assert w.get_save_function_and_args() == (None, None, [])
+    assert w.retrieve_write_results() == []
+    with pytest.raises(NotImplementedError):
+        w.write_data(None, None)
