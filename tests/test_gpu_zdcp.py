@@ -40,7 +40,10 @@ def test_dcp_async_on_engine_matches_sync(tmp_path, dist_1rank, persistent):
             state = _state(step)
             sync_dir, async_dir = tmp_path / f"sync{step}", tmp_path / f"async{step}"
             threads = 1 + step  # one thread is the case where stock PyTorch would pick its CUDA copy-ahead loader
-            dcp.save(state, storage_writer=FileSystemWriter(sync_dir, thread_count=threads), planner=DefaultSavePlanner())
+            # (that loader orders the records of a file by size; per_thread_copy_ahead=0 selects the plan-order loader the
+            # async writer uses, so that the files can be compared byte for byte)
+            sync_writer = FileSystemWriter(sync_dir, thread_count=threads, per_thread_copy_ahead=0)
+            dcp.save(state, storage_writer=sync_writer, planner=DefaultSavePlanner())
             writer = FileSystemWriterAsync(async_dir, thread_count=threads)
             ret = save_state_dict_async_plan(state, writer, None, 0, planner=DefaultSavePlanner())
             assert writer._snapshot is not None and len(writer._payload["cuda_indices"]) == 8
