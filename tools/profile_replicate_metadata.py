@@ -1,0 +1,68 @@
+"""Host-side (metadata) cost of CliqueReplicationStrategy.replicate, measured without a GPU: F gloo ranks, the C2 structure
+(1455 tensors per rank) with tiny payloads so that only pickling / object gathers / skeleton handling are timed.
+
+    python tools/profile_replicate_metadata.py --ranks 8 --iters 5
+"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "nvidia-resiliency-ext_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+
+def c2_like_state(rank, numel=4):
+    import torch
+
+    g = torch.Generator().manual_seed(rank)
+    names = []
+    for layer in range(32):
+        names += [f"layers.{layer}.{n}" for n in ("q", "k", "v", "o", "gate", "up", "down", "ln1", "ln2")]
+    names += ["embed", "final_ln", "lm_head"]
+    model = {n: torch.randn(numel, generator=g) for n in names}
+    opt = {i: {"main_param": torch.randn(numel, generator=g), "exp_avg": torch.randn(numel, generator=g),
+               "exp_avg_sq": torch.rand(numel, generator=g), "step": torch.tensor(float(rank))} for i in range(len(names))}
+    return {"model": model, "optimizer": {"state": opt}, "iteration": 0}
+
+
+def job(rank, world, iters):
+    import torch.distributed as dist
+
+    from _cpu_tasd import CpuTensorAwareStateDict
+    from nvidia_resiliency_ext.checkpointing.local.replication.strategies import CliqueReplicationStrategy
+
+    strat = CliqueReplicationStrategy(dist.group.WORLD, target_device="cpu")
+    for it in range(iters):
+        sd = c2_like_state(rank)
+        sd["iteration"] = it  # a changing non-tensor leaf, as a trainer would have
+        tasd = CpuTensorAwareStateDict(sd)
+        dist.barrier()
+        prof = None
+        if rank == 0 and it == iters - 1 and os.environ.get("PROFILE"):
+            import cProfile
+
+            prof = cProfile.Profile()
+            prof.enable()
+        t0 = time.perf_counter()
+        out, ids = strat.replicate(tasd, f"id{it}_{rank}")
+        dt = time.perf_counter() - t0
+        if prof is not None:
+            import pstats
+
+            prof.disable()
+            pstats.Stats(prof).sort_stats("cumulative").print_stats(25)
+        assert len(out) == world and not out[0].is_hollow
+        if rank == 0:
+            print(f"iter {it}: replicate host time {dt * 1e3:.1f} ms", flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ranks", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=5)
+    a = ap.parse_args()
+    from _mp import run_ranks
+
+    run_ranks(job, a.ranks, a.iters)
