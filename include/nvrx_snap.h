@@ -175,7 +175,9 @@ int nvrx_stream_wait_u64_geq(void* stream, void* addr, uint64_t value);
  * mp.Queue to the persistent worker (async_ckpt/core.py:541): ONE persistent POSIX shared-memory
  * mapping, page-locked with cudaHostRegister, that the writer process maps by name.
  *   shm_name   "/name" for shm_open, or NULL for an anonymous MAP_SHARED mapping (fork-inheritable)
- *   bytes      payload capacity (a 4096-byte header page precedes the payload inside the mapping)
+ *   bytes      payload capacity (a 4096-byte header page precedes the payload inside the mapping; the page begins with a
+ *              ZIP local file header of an empty record, so that a slot packed in checkpoint-container geometry can be
+ *              published as a torch.load-able file by a hard link, and holds the progress word at byte 192)
  *   prefault_threads  >0: touch pages with that many threads before pinning
  *   pin        0: map only (CPU-only process / no GPU), 1: cudaHostRegister for `device`
  */

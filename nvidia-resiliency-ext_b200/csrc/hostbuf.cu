@@ -1,5 +1,8 @@
 // hostbuf.cu -- host snapshot buffers of the C ABI: one POSIX shared-memory mapping per snapshot slot,
 // page-locked for DMA, followed by CPU-only processes through a progress word in its header page.
+//
+// Layout of the shm object:  [ header page, 4096 B ][ payload, capacity B ]
+// The header page starts with a ZIP local file header (see write_slot_prefix) and carries the Header struct at byte 128.
 #include <cuda_runtime.h>
 #include <ctype.h>
 #include <errno.h>
@@ -36,6 +39,44 @@ struct Header {
     uint8_t pad1[56];
 };
 static_assert(sizeof(Header) == 128, "header layout");
+constexpr uint64_t kHeaderOff = 128;  // where the Header struct sits inside the header page
+
+inline Header* header_of(uint8_t* map) { return reinterpret_cast<Header*>(map + kHeaderOff); }
+
+void put16(uint8_t* p, uint16_t v) {
+    p[0] = static_cast<uint8_t>(v);
+    p[1] = static_cast<uint8_t>(v >> 8);
+}
+void put32(uint8_t* p, uint32_t v) {
+    put16(p, static_cast<uint16_t>(v));
+    put16(p + 2, static_cast<uint16_t>(v >> 16));
+}
+
+// The header page doubles as a ZIP local file header: an empty stored record named ".nvrx_slot" whose *extra field* spans
+// the rest of the page (and so contains the Header struct).  A slot whose payload was packed in checkpoint-container
+// geometry (checkpointing/b200/ptzip.py) can then be published as a torch.load-able file by writing the container's tail and
+// adding a hard link to the shm object -- torch.load insists on "PK\3\4" as the first four bytes of a checkpoint.  The
+// record is not listed in any central directory; readers that walk local headers see a zero-length file.
+void write_slot_prefix(uint8_t* page) {
+    static const char name[] = ".nvrx_slot";
+    const uint16_t name_len = static_cast<uint16_t>(sizeof(name) - 1);
+    const uint16_t extra_len = static_cast<uint16_t>(kHeaderBytes - 30 - name_len);
+    put32(page + 0, 0x04034b50u);  // local file header signature
+    put16(page + 4, 20);           // version needed
+    put16(page + 6, 0);            // flags
+    put16(page + 8, 0);            // method: stored
+    put16(page + 10, 0);           // time
+    put16(page + 12, 0x21);        // date 1980-01-01
+    put32(page + 14, 0);           // crc32 of no bytes
+    put32(page + 18, 0);           // compressed size
+    put32(page + 22, 0);           // uncompressed size
+    put16(page + 26, name_len);
+    put16(page + 28, extra_len);
+    memcpy(page + 30, name, name_len);
+    put16(page + 30 + name_len, 0x4246);  // "FB": the extra-field id PyTorch uses for alignment padding
+    put16(page + 32 + name_len, static_cast<uint16_t>(extra_len - 4));
+    static_assert(30 + sizeof(name) - 1 + 4 <= kHeaderOff, "zip prefix must end before the Header struct");
+}
 
 // CPUs of the NUMA node the GPU hangs off (empty set if sysfs does not say): the slot is first-touched from
 // those CPUs so its pages land in the DRAM next to the GPU's PCIe root port and the drain does not cross sockets.
@@ -220,7 +261,8 @@ int nvrx_hostbuf_create(const char* shm_name, uint64_t bytes, int prefault_threa
         const bool local = pin && !getenv("NVRX_B200_NO_NUMA") && numa_cpus_of_device(device, &cpus);
         prefault(hb->map, total, prefault_threads, local ? &cpus : nullptr);
     }
-    Header* h = reinterpret_cast<Header*>(hb->map);
+    write_slot_prefix(hb->map);
+    Header* h = header_of(hb->map);
     h->magic = kMagic;
     h->capacity = hb->capacity;
     h->progress = 0;
@@ -253,7 +295,7 @@ int nvrx_hostbuf_open(const char* shm_name, nvrx_hostbuf** out) {
     void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
     if (m == MAP_FAILED) return NVRX_E_SYS;
-    const Header* h = static_cast<const Header*>(m);
+    const Header* h = header_of(static_cast<uint8_t*>(m));
     if (h->magic != kMagic || h->capacity != total - kHeaderBytes) {
         munmap(m, total);
         return NVRX_E_STATE;
@@ -289,7 +331,7 @@ void* nvrx_hostbuf_data(nvrx_hostbuf* hb) { return hb ? hb->map + kHeaderBytes :
 uint64_t nvrx_hostbuf_capacity(const nvrx_hostbuf* hb) { return hb ? hb->capacity : 0; }
 
 volatile uint64_t* nvrx_hostbuf_progress(nvrx_hostbuf* hb) {
-    return hb ? &reinterpret_cast<Header*>(hb->map)->progress : nullptr;
+    return hb ? &header_of(hb->map)->progress : nullptr;
 }
 
 int nvrx_hostbuf_wait(nvrx_hostbuf* hb, uint64_t value, int64_t timeout_ms) {

@@ -415,6 +415,14 @@ class _Slot:
     drained_total: int = 0  # cumulative bytes the progress word has been advanced by
     done_event: Optional[Event] = None
 
+    def published(self) -> bool:
+        """A checkpoint file is a hard link to this slot (zero-copy persistence): its pages must not be overwritten."""
+        if self.buf is None or not self.buf.name:
+            return False
+        from .ptzip import slot_is_published
+
+        return slot_is_published("/dev/shm" + self.buf.name)
+
 
 @dataclass
 class Snapshot:
@@ -468,6 +476,23 @@ class Snapshot:
         if not self.released:
             self.released = True
             self.engine._release(self.slot)
+
+
+def choose_slot(slots: Sequence[_Slot], nbytes: int, max_slots: int) -> Tuple[Optional[_Slot], bool]:
+    """Which slot the next snapshot of ``nbytes`` goes to: ``(slot, retire)``.
+
+    Prefer an idle slot that is already large enough (no re-pinning), then any idle slot.  A slot that was published as a
+    checkpoint file (hard link, zero-copy persistence) is idle again once that file has been deleted; while the file exists
+    it is skipped.  ``(None, False)`` = grow the pool if allowed; ``retire`` = the pool is at its bound and every idle slot
+    is a checkpoint somebody keeps, so one of them has to be given up to the file system."""
+    idle = [s for s in slots if not s.busy]
+    free = [s for s in idle if not s.published()]
+    pick = next((s for s in free if s.buf is not None and s.buf.capacity >= nbytes), free[0] if free else None)
+    if pick is None and len(slots) >= max_slots:
+        kept = next((s for s in idle if s.published()), None)
+        if kept is not None:
+            return kept, True
+    return pick, False
 
 
 class SnapshotEngine:
@@ -545,9 +570,12 @@ class SnapshotEngine:
 
     def _acquire_slot(self, nbytes: int, slot: Optional[_Slot] = None) -> _Slot:
         if slot is None:
-            # prefer a free slot that is already large enough (no re-pinning), then any free slot
-            free = [s for s in self._slots if not s.busy]
-            slot = next((s for s in free if s.buf is not None and s.buf.capacity >= nbytes), free[0] if free else None)
+            slot, retire = choose_slot(self._slots, nbytes, self.max_host_slots)
+            if retire:
+                # the pool is full of checkpoints somebody keeps: give this one up (the file keeps the pages, this process
+                # drops its mapping and pinning) and start a fresh buffer in its place
+                slot.buf.close()
+                slot.buf = None
         if slot is None and len(self._slots) < self.max_host_slots:
             # every slot still belongs to an unfinalized save: grow the pool (the reference allocates fresh pinned
             # memory for every save, too); bounded so a caller that never finalizes fails loudly instead of eating RAM
@@ -582,21 +610,31 @@ class SnapshotEngine:
         16 GB takes seconds; do it once at start-up instead of inside the first save)."""
         self._ensure_staging(nbytes)
         for s in self._slots:
-            if not s.busy:
+            if not s.busy and not s.published():
                 self._acquire_slot(nbytes, s)
                 self._release(s)
 
     # ---- planning -------------------------------------------------------------------------------
-    def _plan_for(self, tensors: Sequence[torch.Tensor], narrow: Sequence[bool]) -> Plan:
+    def _plan_for(self, tensors: Sequence[torch.Tensor], narrow: Sequence[bool], container: bool = False) -> Plan:
+        """Cached plan for tensors of these sizes/dtypes.  ``container``: staging offsets follow the checkpoint-container
+        geometry of ``ptzip.slot_offsets`` (room for a ZIP local header in front of every segment) instead of the dense
+        default, so that the drained slot can be published as a file without a copy."""
         key = tuple((t.numel() * t.element_size(), t.dtype, nr) for t, nr in zip(tensors, narrow))
+        if container:
+            key = ("container",) + key
         ptrs = [t.data_ptr() if t.numel() else 0 for t in tensors]
         plan = self._plans.get(key)
         if plan is None:
-            nbytes = [k[0] for k in key]
+            nbytes = [t.numel() * t.element_size() for t in tensors]
             flags = [_cabi.SEG_NARROW_F32_BF16 if nr else 0 for nr in narrow]
+            offsets = None
+            if container:
+                from .ptzip import slot_offsets
+
+                offsets, _ = slot_offsets([nb // 2 if nr else nb for nb, nr in zip(nbytes, narrow)])
             plan = Plan(
                 ptrs, nbytes, flags, device=self.device, align=self.align, tile_bytes=self.tile_bytes,
-                variant=self.variant,
+                variant=self.variant, staging_offsets=offsets,
             )
             self._plans[key] = plan
         else:
@@ -608,10 +646,11 @@ class SnapshotEngine:
         return [bool(narrow) and t.dtype == torch.float32 and t.numel() > 0 for t in tensors]
 
     # ---- snapshot -------------------------------------------------------------------------------
-    def snapshot(self, tensors: Sequence[torch.Tensor], *, narrow: bool = False) -> Snapshot:
+    def snapshot(self, tensors: Sequence[torch.Tensor], *, narrow: bool = False, container: Optional[bool] = None) -> Snapshot:
         """Pack ``tensors`` (CUDA tensors of this device; others pass through) and start the drain.
 
-        Returns as soon as the pack kernel and the side-stream copy are *enqueued*."""
+        Returns as soon as the pack kernel and the side-stream copy are *enqueued*.  ``container`` (default: the
+        ``NVRX_B200_ZERO_COPY`` switch) packs in checkpoint-container geometry, see :meth:`_plan_for`."""
         all_tensors = list(tensors)
         passthrough = {i: t for i, t in enumerate(all_tensors) if not (t.is_cuda and t.device.index == self.device)}
         cuda_tensors = [t for i, t in enumerate(all_tensors) if i not in passthrough] if passthrough else all_tensors
@@ -619,11 +658,21 @@ class SnapshotEngine:
         if not all(t.is_contiguous() for t in cuda_tensors):
             cuda_tensors = [t if t.is_contiguous() else t.detach().contiguous() for t in cuda_tensors]
         mask = self._narrow_mask(cuda_tensors, narrow)
-        plan = self._plan_for(cuda_tensors, mask)
+        if container is None:
+            from .fastsave import zero_copy_enabled
+
+            container = zero_copy_enabled()
+        container = bool(container) and not passthrough and len(cuda_tensors) > 0
+        plan = self._plan_for(cuda_tensors, mask, container)
 
         stream = self._current_stream()
         staging = self._ensure_staging(plan.staging_bytes)
-        slot = self._acquire_slot(plan.staging_bytes)
+        tail_room = 0
+        if container:
+            from .ptzip import slot_tail_room
+
+            tail_room = slot_tail_room(len(cuda_tensors))
+        slot = self._acquire_slot(plan.staging_bytes + tail_room)
         if self._staging_free is not None:
             # the previous drain may still be reading staging: order the pack after it on the GPU
             stream_wait_event(stream, self._staging_free)

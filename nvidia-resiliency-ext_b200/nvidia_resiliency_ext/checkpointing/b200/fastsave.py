@@ -73,8 +73,40 @@ def _locate(ptr: int, nbytes: int):
     return None, 0
 
 
+def zero_copy_enabled() -> bool:
+    """Opt-in (``NVRX_B200_ZERO_COPY=1``): snapshots are packed in checkpoint-container geometry and a save whose target
+    shares a file system with the slots (``/dev/shm``) publishes the slot with a hard link instead of copying it."""
+    return os.environ.get("NVRX_B200_ZERO_COPY", "0") == "1"
+
+
+def _try_link(obj, target: str, records, protocol) -> bool:
+    """Publish the snapshot slot itself as the checkpoint file (``ptzip.publish_slot``) when every tensor of ``obj`` lives
+    in ONE named slot, in storage order, at the container's offsets.  False = nothing published, copy instead."""
+    from . import ptzip
+
+    if [r[0] for r in records] != [f"data/{i}" for i in range(len(records))]:
+        return False
+    slot, offsets, sizes = None, [], []
+    for _, ptr, nbytes in records:
+        hb, off = _locate(ptr, nbytes) if nbytes else (slot, 0)
+        if nbytes:
+            if hb is None or not hb.name or (slot is not None and hb.name != slot.name):
+                return False
+            slot = hb
+        offsets.append(off)
+        sizes.append(nbytes)
+    if slot is None:
+        return False
+    crcs = None
+    if os.environ.get("NVRX_B200_ZIP_CRC", "0") not in ("", "0"):
+        crcs = [slot.crc32(off, nb, WRITE_THREADS) if nb else 0 for off, nb in zip(offsets, sizes)]
+    small = ptzip.small_records(obj, protocol)
+    return ptzip.publish_slot("/dev/shm" + slot.name, target, small, offsets, sizes, crcs=crcs)
+
+
 def save(obj, f, *args, **kwargs) -> str:
-    """Drop-in for ``torch.save(obj, f, ...)``.  Returns which path was taken: "parallel" or "torch"."""
+    """Drop-in for ``torch.save(obj, f, ...)``.  Returns which path was taken: "linked" (zero-copy publish of the slot),
+    "parallel" (container by PyTorch, payload by the slot's writer pool) or "torch"."""
     if not _active_ranges or args or set(kwargs) - {"pickle_protocol"} or not hasattr(torch.serialization, "skip_data"):
         torch.save(obj, f, *args, **kwargs)
         return "torch"
@@ -89,6 +121,11 @@ def save(obj, f, *args, **kwargs) -> str:
 
     is_path = isinstance(f, (str, os.PathLike))
     start = 0 if is_path else f.tell()
+    if zero_copy_enabled() and start == 0:
+        target = os.fspath(f) if is_path else getattr(f, "name", None)
+        # a file object was opened (exclusively, by the managers) on its name: the link replaces that empty file
+        if isinstance(target, str) and _try_link(obj, target, records, protocol):
+            return "linked"
     with torch.serialization.skip_data():
         torch.save(obj, f, **kwargs)
     if not is_path:

@@ -70,23 +70,25 @@ def _local_header(name: bytes, size: int, crc: int, data_off_hint: int, header_o
     return hdr + name + extra
 
 
-def _data_offset_after(header_off: int, name_len: int, zip64: bool) -> int:
-    """Smallest ALIGN-aligned data offset that leaves room for the header (+ zip64 extra) and a legal padding field."""
+def _data_offset_after(header_off: int, name_len: int, zip64: bool, align: int = ALIGN) -> int:
+    """Smallest ``align``-aligned data offset that leaves room for the header (+ zip64 extra) and a legal padding field."""
     need = header_off + 30 + name_len + (20 if zip64 else 0)
-    off = -(-need // ALIGN) * ALIGN
+    off = -(-need // align) * align
     while 0 < off - need < 4:  # a padding extra field needs at least its 4-byte header
-        off += ALIGN
+        off += align
     return off
 
 
-def plan_payload(archive: str, sizes: Sequence[int], *, start: int = 0, force_zip64: bool = False) -> PayloadLayout:
-    """Lay out ``data/<i>`` records of the given sizes starting at file offset ``start``."""
+def plan_payload(archive: str, sizes: Sequence[int], *, start: int = 0, force_zip64: bool = False, align: int = ALIGN) -> PayloadLayout:
+    """Lay out ``data/<i>`` records of the given sizes starting at file offset ``start``; record data is aligned to
+    ``align`` (a multiple of PyTorch's 64)."""
+    assert align % ALIGN == 0
     lay = PayloadLayout(archive=archive)
     cur = start
     for i, size in enumerate(sizes):
         name = f"{archive}/data/{i}"
         zip64 = force_zip64 or size >= _U32
-        data_off = _data_offset_after(cur, len(name.encode()), zip64)
+        data_off = _data_offset_after(cur, len(name.encode()), zip64, align)
         lay.records.append(Record(name=name, size=size, header_off=cur, data_off=data_off))
         cur = data_off + size
     lay.end = cur
@@ -116,13 +118,7 @@ def describe(obj: Any, protocol: int = torch.serialization.DEFAULT_PROTOCOL) -> 
     torch.serialization._save(obj, rec, pickle, protocol, False)
     keys = [int(n.split("/", 1)[1]) for n, _, _ in rec.storages]
     assert keys == list(range(len(keys))), "storage keys are expected to be 0..n-1 in order"
-    buf = io.BytesIO()
-    with torch.serialization.skip_data():
-        torch.save(obj, buf, pickle_protocol=protocol)
-    buf.seek(0)
-    reader = torch._C.PyTorchFileReader(buf)
-    small = [(n, bytes(reader.get_record(n))) for n in reader.get_all_records() if not n.startswith("data/")]
-    return small, [(ptr, nb) for _, ptr, nb in rec.storages]
+    return small_records(obj, protocol), [(ptr, nb) for _, ptr, nb in rec.storages]
 
 
 def _central_entry(name: bytes, size: int, crc: int, header_off: int, force_zip64: bool) -> bytes:
@@ -159,6 +155,16 @@ def _crc_of_file_range(fd: int, off: int, n: int) -> int:
     return crc & _U32
 
 
+def small_records(obj: Any, protocol: int = torch.serialization.DEFAULT_PROTOCOL) -> List[Tuple[str, bytes]]:
+    """Everything PyTorch writes for ``obj`` besides tensor data (``data.pkl``, ``byteorder``, ``version``, ...)."""
+    buf = io.BytesIO()
+    with torch.serialization.skip_data():
+        torch.save(obj, buf, pickle_protocol=protocol)
+    buf.seek(0)
+    reader = torch._C.PyTorchFileReader(buf)
+    return [(n, bytes(reader.get_record(n))) for n in reader.get_all_records() if not n.startswith("data/")]
+
+
 def tail_size(archive: str, small: Sequence[Tuple[str, bytes]], n_storages: int, force_zip64: bool = False) -> int:
     """Upper bound of the bytes needed after the payload region (small records + pad record + directory + EOCDs)."""
     names = [f"{archive}/{n}" for n, _ in small] + [f"{archive}/data/{i}" for i in range(n_storages)] + [f"{archive}/.pad"]
@@ -176,6 +182,7 @@ def write_container(
     crcs: Optional[Sequence[int]] = None,
     write_payload: Optional[Callable[[Record], None]] = None,
     force_zip64: bool = False,
+    pad_crc: bool = True,
 ) -> int:
     """Write headers, small records, pad record, central directory and EOCDs around a payload region planned by
     :func:`plan_payload`.  Payload bytes themselves are NOT written unless ``write_payload(record)`` is given (they may
@@ -220,9 +227,9 @@ def write_container(
         slack += pad_central_len - len(pad_entry)
         # the pad covers whatever the file holds there (zeros in a fresh file, stale bytes in a reused slot); its crc is
         # only computed when that is cheap -- nothing ever reads the record, it exists to keep the EOCD at the file end
-        pad_crc = _crc_of_file_range(fd, data_off, slack) if slack <= _PAD_CRC_LIMIT else 0
-        pad_entry = _central_entry(name, slack, pad_crc, cur, True)
-        os.pwrite(fd, _local_header(name, slack, pad_crc, data_off, cur, True), cur)
+        pad_sum = _crc_of_file_range(fd, data_off, slack) if pad_crc and slack <= _PAD_CRC_LIMIT else 0
+        pad_entry = _central_entry(name, slack, pad_sum, cur, True)
+        os.pwrite(fd, _local_header(name, slack, pad_sum, data_off, cur, True), cur)
         cd_bytes += pad_entry
         n_entries += 1
         cur = data_off + slack
@@ -278,3 +285,79 @@ def save(obj: Any, path, *, locate: Callable[[int, int], Optional[Tuple[Any, int
     finally:
         os.close(fd)
     return layout
+
+
+# --------------------------------------------------------------------------------------------------
+# slot geometry: a snapshot slot that is a checkpoint file
+# --------------------------------------------------------------------------------------------------
+# A host snapshot slot is a POSIX shm object = a file on the /dev/shm tmpfs: [ 4096-byte header page | payload ].  The
+# header page starts with a ZIP local file header (csrc/hostbuf.cu::write_slot_prefix), so when the payload region was
+# packed at the offsets ``slot_offsets`` gives, the slot becomes a valid checkpoint by writing headers into the gaps and the
+# tail at the end of the file -- and is *published* with a hard link instead of a copy.
+SLOT_PREFIX = 4096
+SLOT_ARCHIVE = "archive"  # what torch.save calls the archive when it is given a buffer
+SLOT_ALIGN = 512  # == the engine's default segment alignment, so the kernels see the geometry they were tuned on
+
+
+def slot_layout(sizes: Sequence[int]) -> PayloadLayout:
+    return plan_payload(SLOT_ARCHIVE, sizes, start=SLOT_PREFIX, align=SLOT_ALIGN)
+
+
+def slot_offsets(sizes: Sequence[int]) -> Tuple[List[int], int]:
+    """Payload-relative offsets for segments of the given (packed) sizes, and the payload bytes they span."""
+    lay = slot_layout(sizes)
+    return [r.data_off - SLOT_PREFIX for r in lay.records], lay.end - SLOT_PREFIX
+
+
+def slot_tail_room(n_storages: int) -> int:
+    """Bytes to keep free after the payload for small records + directory.  A guess (the pickle is not known when the slot
+    is sized); a tail that does not fit makes ``publish_slot`` decline and the caller copies instead."""
+    return (1 << 20) + 1024 * n_storages
+
+
+def publish_slot(
+    slot_path: str,
+    target: str,
+    small: Sequence[Tuple[str, bytes]],
+    offsets: Sequence[int],
+    sizes: Sequence[int],
+    *,
+    crcs: Optional[Sequence[int]] = None,
+) -> bool:
+    """Turn the slot file ``slot_path`` into the checkpoint ``target`` without copying its payload.
+
+    ``offsets[i]`` / ``sizes[i]``: where storage ``i`` sits in the payload region.  Returns False (nothing changed that
+    matters: only bytes outside the storages are written) when the geometry is not the container's, the tail does not
+    fit, or the two paths cannot be hard-linked (different file systems).  An existing ``target`` is replaced atomically."""
+    lay = slot_layout(sizes)
+    for rec, off, size in zip(lay.records, offsets, sizes):
+        if size and off != rec.data_off - SLOT_PREFIX:
+            return False
+    try:
+        fd = os.open(slot_path, os.O_RDWR)
+    except OSError:
+        return False
+    try:
+        file_size = os.fstat(fd).st_size
+        if lay.end + tail_size(SLOT_ARCHIVE, small, len(sizes)) > file_size:
+            return False
+        write_container(fd, lay, small, file_size=file_size, crcs=crcs, pad_crc=False)
+    finally:
+        os.close(fd)
+    tmp = f"{target}.nvrx{os.getpid()}"
+    try:
+        if os.path.lexists(tmp):
+            os.unlink(tmp)
+        os.link(slot_path, tmp)
+        os.replace(tmp, target)
+    except OSError:
+        return False
+    return True
+
+
+def slot_is_published(slot_path: str) -> bool:
+    """True while some checkpoint file is a hard link to this slot (its pages must not be overwritten)."""
+    try:
+        return os.stat(slot_path).st_nlink > 1
+    except OSError:
+        return False
