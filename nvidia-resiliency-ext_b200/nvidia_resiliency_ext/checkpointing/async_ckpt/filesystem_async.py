@@ -36,7 +36,7 @@ from torch.distributed.checkpoint import FileSystemWriter
 from torch.distributed.checkpoint.metadata import Metadata
 from torch.distributed.checkpoint.planner import SavePlan, SavePlanner, WriteItem, WriteItemType
 from torch.distributed.checkpoint.storage import WriteResult
-from torch.distributed.checkpoint.utils import _wrap_exception
+from torch.distributed.checkpoint.utils import _is_wrapped_exception, _wrap_exception
 
 from ..b200.persist import drain_aware
 
@@ -216,6 +216,14 @@ class FileSystemWriterAsync(FileSystemWriter):
             finally:
                 for item in stash:
                     self.results_queue.put(item)
+            if _is_wrapped_exception(outcome):
+                # same wording as the reference (``filesystem_async.py:1199``) so callers matching on it keep working
+                try:
+                    raise RuntimeError(f"Worker failure: {outcome[0]}") from outcome[0]
+                except RuntimeError as exc:
+                    return _wrap_exception(exc)
+            if self.has_data_to_write and len(outcome) == 0:
+                return _wrap_exception(RuntimeError(f"rank {rank}: the writer reported no results for a non-empty plan"))
             return outcome
         finally:
             if self._snapshot is not None:
