@@ -16,9 +16,13 @@ one pinned shared-memory slot.  The write function (run by the async worker) map
 progress word, and then lets PyTorch's own ``FileSystemWriter.write_data`` produce the files from the host views -- the
 on-disk format is PyTorch's, byte for byte (``tests/test_dcp_async_cpu.py`` compares against a synchronous ``dcp.save``).
 
-Not carried over (accepted for signature compatibility, documented no-ops): ``use_msc`` (multistorageclient),
+``separation_hint`` works as in the reference (``:1350``): items whose FQN starts with the hint go to files of their own,
+named ``<hint>__<rank>_<n>.distcp``, and ``thread_count`` must then be at least 2.  Quantized CUDA tensors that offer
+``dequantize()`` are dequantized before staging (``:253``).
+
+Not carried over (accepted for signature compatibility, documented no-ops): ``use_msc`` (multistorageclient, raises),
 ``is_multiproc_io`` (file IO is multi-threaded through ``thread_count``), ``use_cached_data_structure`` and
-``use_cpu_shm_for_gpu_tensors`` (the engine's plan cache and shm slot make both moot), ``separation_hint``.
+``use_cpu_shm_for_gpu_tensors`` (the engine's plan cache and shm slot make both moot).
 """
 
 from __future__ import annotations
@@ -72,6 +76,25 @@ def _passthrough(payload):
     return payload
 
 
+def _write_separated(writer: FileSystemWriter, plan: SavePlan, planner, hint: str):
+    """``FileSystemWriter.write_data`` with the items split by ``hint``: half as many size-balanced buckets as threads, each
+    bucket divided into "FQN starts with the hint" and the rest, one file per non-empty part; files of the hinted part carry
+    the hint in front of the usual ``__<rank>_`` prefix."""
+    from torch.distributed.checkpoint.filesystem import DEFAULT_SUFFIX, _split_by_size_and_type
+
+    buckets = _split_by_size_and_type(max(1, writer.thread_count // 2), plan.items)
+    files: "queue_mod.Queue" = queue_mod.Queue()
+    count = 0
+    for group in ("", hint):
+        for bucket in buckets:
+            part = [it for it in bucket if it.index.fqn.startswith(hint) == bool(group)]
+            if part:
+                name = f"{group}{plan.storage_data.prefix}{count}{DEFAULT_SUFFIX}"
+                count += 1
+                files.put((writer.fs.concat_path(writer.path, name), name, part))
+    return writer._write_data(planner, files)
+
+
 class FileSystemWriterAsync(FileSystemWriter):
     """Async-capable DCP filesystem writer.  One instance per checkpoint save (state is kept between the stages).
 
@@ -113,6 +136,8 @@ class FileSystemWriterAsync(FileSystemWriter):
         """Resolve every write item; CUDA tensors are snapshotted together (pack kernel + drain into one shm slot), host
         tensors and byte blobs are kept as they are.  Returns after the GPU work is *enqueued*."""
         t0 = time()
+        if self.separation_hint:
+            assert self.thread_count > 1, "thread_count must be at least 2 if separation_hint is provided"
         staged_host: Dict = {}
         cuda_items: List[WriteItem] = []
         cuda_tensors: List[torch.Tensor] = []
@@ -123,6 +148,8 @@ class FileSystemWriterAsync(FileSystemWriter):
             else:
                 ten = data.detach()
                 if ten.is_cuda:
+                    if "dequantize" in type(ten).__dict__:  # quantized wrapper tensors are stored dequantized
+                        ten = ten.dequantize()
                     cuda_items.append(item)
                     cuda_tensors.append(ten)
                 else:
@@ -151,12 +178,12 @@ class FileSystemWriterAsync(FileSystemWriter):
             return None, None, []
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.results_queue = get_write_results_queue()
-        save_fn = drain_aware(partial(self.write_preloaded_data, self._ctor, int(self.thread_count)))
+        save_fn = drain_aware(partial(self.write_preloaded_data, self._ctor, int(self.thread_count), self.separation_hint))
         return save_fn, partial(_passthrough, self._payload), [rank, None, self.results_queue]
 
     # ---- stage 2 (writer process) -------------------------------------------------------------------
     @staticmethod
-    def write_preloaded_data(ctor, thread_count: int, rank: int, payload: dict, results_queue) -> None:
+    def write_preloaded_data(ctor, thread_count: int, separation_hint, rank: int, payload: dict, results_queue) -> None:
         """Write the files of this rank with PyTorch's ``FileSystemWriter`` from staged host data; the outcome (list of
         ``WriteResult`` or a wrapped exception) is reported on ``results_queue``.  Never raises."""
         outcome = None
@@ -183,7 +210,10 @@ class FileSystemWriterAsync(FileSystemWriter):
             # everything is on the host already: keep PyTorch off its CUDA copy-ahead loader (it would create a CUDA
             # context in the writer process, or fail in a forked one)
             writer.per_thread_copy_ahead = 0
-            outcome = writer.write_data(payload["plan"], _HostPlanner(staged)).wait()
+            if separation_hint:
+                outcome = _write_separated(writer, payload["plan"], _HostPlanner(staged), separation_hint).wait()
+            else:
+                outcome = writer.write_data(payload["plan"], _HostPlanner(staged)).wait()
             if outcome is None:
                 outcome = []
         except BaseException as exc:  # noqa: BLE001 - reported to the trainer, raised there on the coordinator

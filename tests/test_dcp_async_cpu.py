@@ -27,7 +27,7 @@ def _state(rank=0, step=0):
     }
 
 
-def _async_save(state, path, queue, planner=None, **kw):
+def _async_save(state, path, queue, planner=None, writer_kw=None, **kw):
     from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncRequest
     from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
     from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import (
@@ -35,7 +35,7 @@ def _async_save(state, path, queue, planner=None, **kw):
         save_state_dict_async_plan,
     )
 
-    writer = FileSystemWriterAsync(path, thread_count=2)
+    writer = FileSystemWriterAsync(path, thread_count=2, **(writer_kw or {}))
     ret = save_state_dict_async_plan(state, writer, None, 0, planner=planner or DefaultSavePlanner(), **kw)
     save_fn, preload_fn, save_args = writer.get_save_function_and_args()
     assert save_fn is not None and getattr(save_fn, "nvrx_drain_aware", False)
@@ -220,7 +220,7 @@ def test_writer_process_reads_cuda_items_from_the_snapshot_slot(tmp_path, built_
         t = threading.Thread(target=drain)
         t.start()
         results = multiprocessing.get_context("spawn").Manager().Queue()
-        FileSystemWriterAsync.write_preloaded_data(writer._ctor, 1, 0, payload, results)
+        FileSystemWriterAsync.write_preloaded_data(writer._ctor, 1, None, 0, payload, results)
         t.join()
         rank, outcome = results.get(timeout=10)
         assert rank == 0 and isinstance(outcome, list) and len(outcome) == len(payload["plan"].items), outcome
@@ -263,3 +263,25 @@ def test_cached_metadata_reader(tmp_path, dist_1rank):
     CachedMetadataFileSystemReader.clear_metadata_cache(tmp_path / "a")
     assert CachedMetadataFileSystemReader(tmp_path / "a").read_metadata() is not first
     CachedMetadataFileSystemReader.clear_metadata_cache()
+
+
+def test_separation_hint_splits_files(tmp_path, dist_1rank):
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+
+    state = _state()
+    q = AsyncCallsQueue(persistent=False)
+    try:
+        _async_save(state, tmp_path / "ckpt", q, writer_kw={"separation_hint": "opt"})
+        q.maybe_finalize_async_calls(blocking=True)
+    finally:
+        q.close()
+    files = sorted(f for f in os.listdir(tmp_path / "ckpt") if f.endswith(".distcp"))
+    assert [f for f in files if f.startswith("opt__0_")] and [f for f in files if f.startswith("__0_")], files
+    md = FileSystemReader(tmp_path / "ckpt").read_metadata()
+    for index, info in md.storage_data.items():
+        assert info.relative_path.startswith("opt") == index.fqn.startswith("opt"), (index, info)
+    _loaded_equals(tmp_path / "ckpt", _state())
+    with pytest.raises(AssertionError, match="thread_count"):
+        w = FileSystemWriterAsync(tmp_path / "x", thread_count=1, separation_hint="opt")
+        w.prepare_write_data(None, None)
