@@ -14,6 +14,9 @@ What is produced (all inputs are seeded and stored next to the outputs):
                                           ``find_latest`` coverage rule and file-name template on fixed scenarios
   replicate_2rank.json                    ``CliqueReplicationStrategy.replicate`` run on a 2-rank gloo group: order of
                                           returned ids and sha256 of every returned tensor, per rank
+  dcp_inputs.pt / dcp_reference/          ``FileSystemWriterAsync`` + ``save_state_dict_async_plan`` + ``AsyncCallsQueue`` +
+                                          ``save_state_dict_async_finalize`` (filesystem_async.py:140, state_dict_saver.py:236,417):
+                                          the DCP checkpoint directory the reference's async writer produces (CPU tensors)
   bf16_cases.npz                          fp32 bit patterns and ``x.to(torch.bfloat16)`` bits from PyTorch (CPU)
 """
 import hashlib
@@ -119,6 +122,53 @@ def gen_local():
             "to_id": list(mgr._filename_to_id("iter_0000042_3_local.pt")),
         }
     return names
+
+
+def dcp_state_dict():
+    g = torch.Generator().manual_seed(11)
+    return {
+        "model": {
+            "w": torch.randn(33, 17, generator=g),
+            "b": torch.arange(7, dtype=torch.int64),
+            "h": torch.randn(5, 3, generator=g).to(torch.bfloat16),
+            "empty": torch.empty(0, 4),
+        },
+        "opt": {"step": torch.tensor(3), "lr": 0.125, "name": "adam"},
+    }
+
+
+def gen_dcp():
+    import shutil
+
+    from torch.distributed.checkpoint import DefaultSavePlanner
+
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue, AsyncRequest
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import (
+        save_state_dict_async_finalize,
+        save_state_dict_async_plan,
+    )
+
+    sd = dcp_state_dict()
+    torch.save(sd, os.path.join(HERE, "dcp_inputs.pt"))
+    out = os.path.join(HERE, "dcp_reference")
+    shutil.rmtree(out, ignore_errors=True)
+    q = AsyncCallsQueue(persistent=True, cpu_shm_mode=True)
+    writer = FileSystemWriterAsync(out, thread_count=2)
+    ret = save_state_dict_async_plan(sd, writer, None, 0, planner=DefaultSavePlanner())
+    save_fn, preload_fn, save_args = writer.get_save_function_and_args()
+    q.schedule_async_request(AsyncRequest(save_fn, save_args, [], preload_fn=preload_fn))
+    q.maybe_finalize_async_calls(blocking=True, no_dist=True)
+    try:
+        save_state_dict_async_finalize(*ret)
+    except RuntimeError as exc:
+        # the reference builds its failure flag on torch.cuda.current_device() (state_dict_saver.py:455-459), which needs a
+        # GPU; that line runs AFTER the coordinator has written .metadata, so the checkpoint on disk is complete
+        assert "NVIDIA driver" in str(exc), exc
+    q.close()
+    assert os.path.exists(os.path.join(out, ".metadata"))
+    with open(os.path.join(out, "torch_version.txt"), "w") as fh:
+        fh.write(torch.__version__)
 
 
 class _StubGroup:
@@ -280,11 +330,17 @@ def gen_bf16():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["dcp"]:  # add the DCP fixture without touching the others
+        init_single_rank()
+        gen_dcp()
+        dist.destroy_process_group()
+        sys.exit(0)
     gen_bf16()
     gen_replicate()
     init_single_rank()
     gen_c1()
     names = gen_local()
     gen_replication(names)
+    gen_dcp()
     dist.destroy_process_group()
     print("golden fixtures written to", HERE)

@@ -285,3 +285,50 @@ def test_separation_hint_splits_files(tmp_path, dist_1rank):
     with pytest.raises(AssertionError, match="thread_count"):
         w = FileSystemWriterAsync(tmp_path / "x", thread_count=1, separation_hint="opt")
         w.prepare_write_data(None, None)
+
+
+def test_matches_the_references_own_async_checkpoint(tmp_path, dist_1rank):
+    """tests/golden/dcp_reference was written by the REFERENCE's FileSystemWriterAsync path (make_golden.py::gen_dcp) for
+    dcp_inputs.pt.  Our writer must produce the same checkpoint: same values when loaded, same metadata, and -- on the
+    PyTorch version the fixture was made with -- the same bytes."""
+    import pickle
+    from dataclasses import fields
+
+    from conftest import GOLDEN
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+
+    state = torch.load(GOLDEN / "dcp_inputs.pt", weights_only=False)
+    q = AsyncCallsQueue(persistent=True)
+    try:
+        _async_save(state, tmp_path / "ours", q)
+        q.maybe_finalize_async_calls(blocking=True)
+    finally:
+        q.close()
+
+    def loaded(path):
+        got = {k: {kk: (torch.zeros_like(vv) if isinstance(vv, torch.Tensor) else None) for kk, vv in v.items()} for k, v in state.items()}
+        dcp.load(got, storage_reader=FileSystemReader(path))
+        return got
+
+    ref, ours = loaded(GOLDEN / "dcp_reference"), loaded(tmp_path / "ours")
+    for k, sub in state.items():
+        for kk, vv in sub.items():
+            if isinstance(vv, torch.Tensor):
+                assert torch.equal(ref[k][kk], vv) and torch.equal(ours[k][kk], vv) and ours[k][kk].dtype == ref[k][kk].dtype
+            else:
+                assert ref[k][kk] == ours[k][kk] == vv
+    mds = []
+    for d in (GOLDEN / "dcp_reference", tmp_path / "ours"):
+        with open(d / ".metadata", "rb") as fh:
+            mds.append(pickle.load(fh))
+    for f in fields(mds[1]):
+        if f.name not in ("storage_data", "storage_meta") and hasattr(mds[0], f.name):
+            assert getattr(mds[0], f.name) == getattr(mds[1], f.name), f.name
+    assert {k: (v.relative_path, v.offset, v.length) for k, v in mds[0].storage_data.items()} == {
+        k: (v.relative_path, v.offset, v.length) for k, v in mds[1].storage_data.items()
+    }
+    if (GOLDEN / "dcp_reference" / "torch_version.txt").read_text() == torch.__version__:
+        names = sorted(f for f in os.listdir(GOLDEN / "dcp_reference") if f.endswith(".distcp"))
+        assert names == sorted(f for f in os.listdir(tmp_path / "ours") if f.endswith(".distcp"))
+        _, mismatch, errors = filecmp.cmpfiles(GOLDEN / "dcp_reference", tmp_path / "ours", names, shallow=False)
+        assert not mismatch and not errors, (mismatch, errors)
