@@ -535,6 +535,7 @@ class SnapshotEngine:
         self.max_host_slots = max(len(self._slots), int(os.environ.get("NVRX_B200_MAX_HOST_SLOTS", "4")))
         self._slot_gen = 0
         self.launches = 0  # kernels launched by this engine (pack + scatter)
+        self.resident_restores = 0  # restores that read a published slot in place (no host copy)
         self._pid = os.getpid()  # forked writers inherit this object; only the creator may tear it down
 
     # ---- singletons per device ------------------------------------------------------------------
@@ -615,20 +616,25 @@ class SnapshotEngine:
                 self._release(s)
 
     # ---- planning -------------------------------------------------------------------------------
-    def _plan_for(self, tensors: Sequence[torch.Tensor], narrow: Sequence[bool], container: bool = False) -> Plan:
+    def _plan_for(
+        self, tensors: Sequence[torch.Tensor], narrow: Sequence[bool], container: bool = False,
+        offsets: Optional[Sequence[int]] = None,
+    ) -> Plan:
         """Cached plan for tensors of these sizes/dtypes.  ``container``: staging offsets follow the checkpoint-container
         geometry of ``ptzip.slot_offsets`` (room for a ZIP local header in front of every segment) instead of the dense
-        default, so that the drained slot can be published as a file without a copy."""
+        default, so that the drained slot can be published as a file without a copy.  ``offsets``: explicit staging
+        offsets (restore straight from a published slot)."""
         key = tuple((t.numel() * t.element_size(), t.dtype, nr) for t, nr in zip(tensors, narrow))
-        if container:
+        if offsets is not None:
+            key = ("at", tuple(offsets)) + key
+        elif container:
             key = ("container",) + key
         ptrs = [t.data_ptr() if t.numel() else 0 for t in tensors]
         plan = self._plans.get(key)
         if plan is None:
             nbytes = [t.numel() * t.element_size() for t in tensors]
             flags = [_cabi.SEG_NARROW_F32_BF16 if nr else 0 for nr in narrow]
-            offsets = None
-            if container:
+            if offsets is None and container:
                 from .ptzip import slot_offsets
 
                 offsets, _ = slot_offsets([nb // 2 if nr else nb for nb, nr in zip(nbytes, narrow)])
@@ -728,10 +734,14 @@ class SnapshotEngine:
         *,
         widen_to: Optional[Sequence[torch.dtype]] = None,
         out: Optional[Sequence[torch.Tensor]] = None,
+        resident: Optional[Tuple[_Slot, Sequence[int]]] = None,
     ) -> List[torch.Tensor]:
         """CPU tensors -> CUDA tensors of this device with one H2D copy and one scatter kernel.
 
-        ``widen_to[i] == torch.float32`` for a bf16 host tensor widens it in the scatter kernel (exact)."""
+        ``widen_to[i] == torch.float32`` for a bf16 host tensor widens it in the scatter kernel (exact).
+        ``resident`` (from :meth:`resident_source`): the tensors' bytes already sit in that pinned slot at those payload
+        offsets (the checkpoint file is a hard link to the slot), so the gather into a pinned buffer is skipped and the
+        H2D reads the slot directly."""
         host_tensors = [t.detach() for t in host_tensors]
         target_dtypes = [
             (widen_to[i] if widen_to is not None and widen_to[i] is not None else t.dtype)
@@ -745,17 +755,25 @@ class SnapshotEngine:
             out = list(out)
             for o, t, td in zip(out, host_tensors, target_dtypes):
                 assert o.is_cuda and o.is_contiguous() and o.dtype == td and o.shape == t.shape
-        plan = self._plan_for(out, mask)
+        if resident is not None:
+            slot, offsets = resident
+            plan = self._plan_for(out, mask, offsets=list(offsets))
+            assert plan.staging_bytes <= slot.buf.capacity and not slot.busy
+            slot.busy = True  # nobody may pick it while the H2D reads it (it is also protected by its link count)
+            self.resident_restores += 1
+        else:
+            plan = self._plan_for(out, mask)
+            slot = self._acquire_slot(plan.staging_bytes)
         staging = self._ensure_staging(plan.staging_bytes)
-        slot = self._acquire_slot(plan.staging_bytes)
         try:
-            # gather the CPU tensors into the pinned slot at the plan's offsets (no-op cost when the
-            # tensors already are views of one packed buffer with this layout)
-            srcs = [t if t.is_contiguous() else t.contiguous() for t in host_tensors]
-            base = slot.buf.data_ptr
-            todo = [(s.data_ptr(), nb, off) for s, off, nb in zip(srcs, plan.offsets, plan.packed_nbytes) if nb and s.data_ptr() != base + off]
-            if todo:
-                slot.buf.gather([x[0] for x in todo], [x[1] for x in todo], [x[2] for x in todo], threads=self.prefault_threads or 8)
+            if resident is None:
+                # gather the CPU tensors into the pinned slot at the plan's offsets (no-op cost when the
+                # tensors already are views of one packed buffer with this layout)
+                srcs = [t if t.is_contiguous() else t.contiguous() for t in host_tensors]
+                base = slot.buf.data_ptr
+                todo = [(s.data_ptr(), nb, off) for s, off, nb in zip(srcs, plan.offsets, plan.packed_nbytes) if nb and s.data_ptr() != base + off]
+                if todo:
+                    slot.buf.gather([x[0] for x in todo], [x[1] for x in todo], [x[2] for x in todo], threads=self.prefault_threads or 8)
             stream = self._current_stream()
             if self._staging_free is not None:
                 stream_wait_event(stream, self._staging_free)
@@ -772,6 +790,26 @@ class SnapshotEngine:
         finally:
             self._release(slot)
         return out
+
+    def resident_source(self, path, host_tensors: Sequence[torch.Tensor]) -> Optional[Tuple[_Slot, List[int]]]:
+        """``(slot, payload offsets)`` when the checkpoint file ``path`` is a hard link to one of this engine's live,
+        pinned slots (zero-copy persistence; e.g. an in-process restart that reloads the checkpoint it wrote itself) and
+        ``host_tensors`` are the tensors ``torch.load(path, mmap=True)`` returned, in file order; else None."""
+        from .ptzip import SLOT_PREFIX, tensor_offsets_in_file
+
+        for slot in self._slots:
+            if slot.buf is None or slot.busy or not slot.buf.name:
+                continue
+            try:
+                if not os.path.samefile("/dev/shm" + slot.buf.name, path):
+                    continue
+            except OSError:
+                continue
+            offs = tensor_offsets_in_file(path, host_tensors)
+            if offs is None or any(o < SLOT_PREFIX for o in offs):
+                return None
+            return slot, [o - SLOT_PREFIX for o in offs]
+        return None
 
     def restore_from_staging(self, plan: Plan, staging_ptr: int) -> None:
         """Scatter a staging buffer that is already on the device (replica retrieval path)."""

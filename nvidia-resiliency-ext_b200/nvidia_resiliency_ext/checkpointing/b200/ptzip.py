@@ -361,3 +361,29 @@ def slot_is_published(slot_path: str) -> bool:
         return os.stat(slot_path).st_nlink > 1
     except OSError:
         return False
+
+
+def tensor_offsets_in_file(path, tensors: Sequence[torch.Tensor]) -> Optional[List[int]]:
+    """File offsets of the data of ``tensors`` -- what ``torch.load(path, mmap=True)`` returned, in record order -- or None
+    when they are not one-record-per-tensor views of a single mapping of that file, ascending, 16-byte aligned."""
+    live = [(i, t) for i, t in enumerate(tensors) if t.numel()]
+    if not live or any(t.is_cuda or not t.is_contiguous() for _, t in live):
+        return None
+    try:
+        reader = torch._C.PyTorchFileReader(os.fspath(path))
+        first_i, first_t = live[0]
+        base = first_t.data_ptr() - reader.get_record_offset(f"data/{first_i}")  # address the file is mapped at
+        for i, t in live:
+            if reader.get_record_offset(f"data/{i}") != t.data_ptr() - base:
+                return None
+    except (RuntimeError, OSError):
+        return None
+    offs, end = [], 0
+    for t in tensors:
+        nb = t.numel() * t.element_size()
+        off = t.data_ptr() - base if nb else -(-end // 16) * 16
+        if off % 16 or off < end:
+            return None
+        offs.append(off)
+        end = off + nb
+    return offs

@@ -141,5 +141,10 @@ class BasicTensorAwareStateDict(TensorAwareStateDict):
         widen_to: Optional[list] = None
         if widen:
             widen_to = [torch.float32 if t.dtype == torch.bfloat16 else None for t in host]
-        moved = iter(SnapshotEngine.get().restore(host, widen_to=widen_to))
+        engine = SnapshotEngine.get()
+        # set by LocalCheckpointManager._load in zero-copy mode: the file may be a hard link to a slot that is still pinned in
+        # this process (in-process restart), in which case the H2D reads the slot and nothing is copied on the host
+        source = self.__dict__.pop("_b200_loaded_from", None)
+        resident = engine.resident_source(source, host) if source is not None and len(host) == len(current) else None
+        moved = iter(engine.restore(host, widen_to=widen_to, resident=resident))
         self._replace_tensors([t if t.is_cuda else next(moved) for t in current])

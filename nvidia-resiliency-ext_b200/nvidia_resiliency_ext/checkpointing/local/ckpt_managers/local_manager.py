@@ -92,7 +92,10 @@ class LocalCheckpointManager(BaseCheckpointManager):
             try:
                 # map the file instead of copying it: tensors are read once more anyway (parallel gather into the
                 # pinned slot, then one H2D + scatter kernel)
-                return torch.load(path, weights_only=False, mmap=True)  # nosec B614 - files are produced by this manager
+                loaded = torch.load(path, weights_only=False, mmap=True)  # nosec B614 - files are produced by this manager
+                if fastsave.zero_copy_enabled() and hasattr(loaded, "__dict__"):
+                    loaded.__dict__["_b200_loaded_from"] = str(path)  # consumed by restore_tensor_device
+                return loaded
             except (RuntimeError, ValueError):
                 return torch.load(path, weights_only=False)  # nosec B614 - legacy (non-zip) or unmappable file
         except FileNotFoundError as exc:

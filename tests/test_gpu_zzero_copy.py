@@ -63,7 +63,11 @@ def test_local_manager_zero_copy_roundtrip(shm_dir, dist_1rank, built_library, m
     from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
     from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
 
+    from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
+
     monkeypatch.setenv("NVRX_B200_ZERO_COPY", "1")
+    engine = SnapshotEngine.get()
+    before = engine.resident_restores
     mgr = LocalCheckpointManager(shm_dir)
     q = AsyncCallsQueue(persistent=False)
     try:
@@ -79,5 +83,8 @@ def test_local_manager_zero_copy_roundtrip(shm_dir, dist_1rank, built_library, m
             assert mgr.find_latest() == it
             loaded, _ = mgr.load()
             assert _equal(loaded.state_dict, _state(100 + it))
+            assert all(t.is_cuda for t in loaded.tensors)
+        # every load found its file to be a live pinned slot and fed the H2D from it (no host-side gather)
+        assert engine.resident_restores == before + 3
     finally:
         q.close()

@@ -127,6 +127,12 @@ def test_save_publishes_the_slot_by_hard_link(built_library, shm_dir, monkeypatc
         _same(torch.load(target, weights_only=False), state)
         _same(torch.load(target, weights_only=False, mmap=True), state)
         _same(torch.load(target, weights_only=True), state)
+        # restore side: the tensors of an mmap load are located inside the file (= inside the still-pinned slot)
+        mapped = orc.flatten_tensors(torch.load(target, weights_only=False, mmap=True))
+        offs = ptzip.tensor_offsets_in_file(target, mapped)
+        want = [4096 + o for o in desc["layout"].offsets]
+        assert offs is not None and all(a == b for a, b, t in zip(offs, want, mapped) if t.numel())
+        assert ptzip.tensor_offsets_in_file(target, orc.flatten_tensors(torch.load(target, weights_only=False))) is None
         with zipfile.ZipFile(target) as zf:
             names = zf.namelist()
             assert "archive/data.pkl" in names and "archive/data/0" in names and "archive/.pad" in names
