@@ -300,7 +300,10 @@ def run_engine(args, rank, world, local):
         loaded = torch.load(path, weights_only=False, mmap=True)
         lt = flatten(loaded)
         widen = [torch.float32 if (args.narrow and t.dtype == torch.bfloat16) else None for t in lt]
-        back = engine.restore(lt, widen_to=widen if args.narrow else None)
+        resident = None
+        if os.environ.get("NVRX_B200_ZERO_COPY") == "1":  # opt-in: the file is a hard link to a slot that is still pinned
+            resident = engine.resident_source(path, lt)
+        back = engine.restore(lt, widen_to=widen if args.narrow else None, resident=resident)
         torch.cuda.synchronize()
         restore_s = max_over_ranks(time.perf_counter() - t0)
         launches += 1
@@ -354,6 +357,7 @@ def run_engine(args, rank, world, local):
         "stall_ms": round(stall_ms, 3),
         "persist_s": round(persist_s, 3) if persist_files else None,
         "persist_GBps": round(world * total / persist_s / 1e9, 2) if persist_files else None,
+        "persist_mode": (("zero-copy link" if os.environ.get("NVRX_B200_ZERO_COPY") == "1" else "parallel copy") if persist_files else None),
         "restore_s": None if restore_s is None else round(restore_s, 3),
         "restore_GBps": None if restore_s is None else round(world * total / restore_s / 1e9, 2),
         "gpu_launches": launches,
