@@ -279,6 +279,7 @@ def run_engine(args, rank, world, local):
     e2e_s = max_over_ranks(median(host_safe))
     stall_ms = max_over_ranks(median(stall)) * 1e3
     persist_s = max_over_ranks(median(persist))
+    linked = bool(persist_files and path.exists() and os.stat(path).st_nlink > 1)  # the file IS the pinned slot (opt-in mode)
     # spot-check the last file against the live state (bit-exact unless narrowed)
     check = "skipped"
     if rank == 0 and not args.no_verify and persist_files:
@@ -357,7 +358,7 @@ def run_engine(args, rank, world, local):
         "stall_ms": round(stall_ms, 3),
         "persist_s": round(persist_s, 3) if persist_files else None,
         "persist_GBps": round(world * total / persist_s / 1e9, 2) if persist_files else None,
-        "persist_mode": (("zero-copy link" if os.environ.get("NVRX_B200_ZERO_COPY") == "1" else "parallel copy") if persist_files else None),
+        "persist_mode": (("zero-copy link" if linked else "parallel copy") if persist_files else None),
         "restore_s": None if restore_s is None else round(restore_s, 3),
         "restore_GBps": None if restore_s is None else round(world * total / restore_s / 1e9, 2),
         "gpu_launches": launches,
