@@ -91,6 +91,36 @@ def test_c2_shape_tile_counts(built_library):
     plan.close()
 
 
+def test_c2_in_container_geometry(built_library):
+    """Zero-copy persistence packs the same state at checkpoint-container offsets (ptzip.slot_offsets): the work-list keeps
+    its shape (same bulk tiles, same ragged tiles), the buffer grows only by the header gaps, and the container's tail fits
+    in the room the engine reserves."""
+    from bench import llama3_8b_shard_shapes
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+
+    sizes = []
+    for _, shp in llama3_8b_shard_shapes():
+        n = 1
+        for d in shp:
+            n *= d
+        sizes.append(n * 4)
+    nbytes, ptrs, cur = [], [], 0x7E0000000000
+    for nb in sizes + [x for nb in sizes for x in (nb, nb, nb, 4)]:
+        nbytes.append(nb); ptrs.append(cur); cur += (nb + 511) // 512 * 512
+    offsets, span = ptzip.slot_offsets(nbytes)
+    dense = plan_for(ptrs, nbytes)
+    at = plan_for(ptrs, nbytes, staging_offsets=offsets)
+    assert list(at.offsets) == offsets and all(o % 512 == 0 for o in offsets)
+    (nb_d, tiles_d), (nb_a, tiles_a) = dense.tiles(), at.tiles()
+    assert nb_d == nb_a and [(t[0], t[1]) for t in tiles_d] == [(t[0], t[1]) for t in tiles_a]
+    assert span <= at.staging_bytes <= dense.staging_bytes + 512 * len(nbytes) + 512
+    # a generous pickle (200 bytes per tensor) still fits behind the payload
+    small = [("data.pkl", b"x" * (200 * len(nbytes))), ("byteorder", b"little"), ("version", b"3\n")]
+    assert ptzip.tail_size(ptzip.SLOT_ARCHIVE, small, len(nbytes)) <= ptzip.slot_tail_room(len(nbytes))
+    dense.close()
+    at.close()
+
+
 def test_planner_rejects_bad_arguments(built_library):
     from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
 
