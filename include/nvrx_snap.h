@@ -210,6 +210,31 @@ int nvrx_hostbuf_gather(nvrx_hostbuf* hb, int64_t n, const void* const* srcs, co
 /* crc32 (zlib polynomial) of a payload range computed with `threads` workers and combined. */
 int nvrx_hostbuf_crc32(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int threads, uint32_t* out);
 
+/* ---- CRC-32 of packed extents on the GPU ----------------------------------------------------------------------------
+ * Replaces the CPU checksum pass of the reference's writer: `torch.save` (async_ckpt/torch_ckpt.py:36-41,
+ * local/ckpt_managers/local_manager.py:117-122) runs miniz' crc32 over every tensor record on one core.  Here a kernel reads
+ * the packed device buffer once more (HBM-bound integer work, one coalesced 16-byte load per lane) and emits one 32-bit
+ * partial value per 64 KiB chunk; the values travel to the host with the snapshot and a CPU-only step chains them into the
+ * zlib-compatible crc32 of every extent (== tensor record).  See csrc/crc_kernels.cuh for the arithmetic.
+ *   offsets[i], nbytes[i]   extent i inside the buffer (those that start 16-byte aligned are summed on the GPU, whole
+ *                           512-byte rows only; the remaining bytes are read from the host copy by nvrx_crc_finish)
+ */
+typedef struct nvrx_crc nvrx_crc;
+int nvrx_crc_create(int64_t n, const uint64_t* offsets, const uint64_t* nbytes, int device, nvrx_crc** out); /* no CUDA call */
+int nvrx_crc_destroy(nvrx_crc* c);
+int nvrx_crc_info(const nvrx_crc* c, uint64_t* n_values); /* partial values one run produces */
+/* Launch on `stream`: partial values of the buffer at dev_base, their D2H copy into host_values (pinned, n_values words)
+ * and then -- optional -- a copy of `ready_value` into *host_ready (pinned), all stream-ordered: a CPU-only process that
+ * sees *host_ready == ready_value may read the values.  The buffer must stay unchanged until that point of the stream. */
+int nvrx_crc_run(nvrx_crc* c, const void* dev_base, uint32_t* host_values, uint64_t* host_ready, uint64_t ready_value,
+                 void* stream);
+/* CPU only (writer process): chain the partial values and the host copy of the left-over bytes (host_base = host copy of
+ * the buffer, same offsets) into out_crcs[i] = crc32 of extent i.  NVRX_E_INVALID if n_values does not match the extents. */
+int nvrx_crc_finish(int64_t n, const uint64_t* offsets, const uint64_t* nbytes, const uint32_t* values, uint64_t n_values,
+                    const void* host_base, uint32_t* out_crcs);
+/* The 4x256-word operator table "feed `which` zero bytes" (4, 16, 512; 0 = one full chunk) -- tooling and tests. */
+int nvrx_crc_operator(uint32_t which, uint32_t* out_1024_words);
+
 #ifdef __cplusplus
 }
 #endif

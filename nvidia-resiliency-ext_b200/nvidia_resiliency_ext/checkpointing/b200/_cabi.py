@@ -77,6 +77,12 @@ EXPORTED_SYMBOLS = (
     "nvrx_hostbuf_writev_fd",
     "nvrx_hostbuf_gather",
     "nvrx_hostbuf_crc32",
+    "nvrx_crc_create",
+    "nvrx_crc_destroy",
+    "nvrx_crc_info",
+    "nvrx_crc_run",
+    "nvrx_crc_finish",
+    "nvrx_crc_operator",
 )
 
 
@@ -158,6 +164,12 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_hostbuf_writev_fd": (_int, [_vp, _i64, P(_u64), P(_u64), P(_u64), _int, _int]),
         "nvrx_hostbuf_gather": (_int, [_vp, _i64, P(_vp), P(_u64), P(_u64), _int]),
         "nvrx_hostbuf_crc32": (_int, [_vp, _u64, _u64, _int, P(_u32)]),
+        "nvrx_crc_create": (_int, [_i64, P(_u64), P(_u64), _int, P(_vp)]),
+        "nvrx_crc_destroy": (_int, [_vp]),
+        "nvrx_crc_info": (_int, [_vp, P(_u64)]),
+        "nvrx_crc_run": (_int, [_vp, _vp, _vp, _vp, _u64, _vp]),
+        "nvrx_crc_finish": (_int, [_i64, P(_u64), P(_u64), _vp, _u64, _vp, P(_u32)]),
+        "nvrx_crc_operator": (_int, [_u32, P(_u32)]),
     }
     assert set(sigs) == set(EXPORTED_SYMBOLS)
     for name, (res, args) in sigs.items():

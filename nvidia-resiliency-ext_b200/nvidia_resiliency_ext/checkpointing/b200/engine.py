@@ -242,6 +242,50 @@ class Event:
             pass
 
 
+class CrcPlan:
+    """Extents of a packed device buffer whose zlib CRC-32s the GPU computes (``nvrx_crc_*``).  Creating it is CUDA-free."""
+
+    def __init__(self, offsets: Sequence[int], nbytes: Sequence[int], device: int):
+        self._lib = _cabi.lib()
+        self._h = C.c_void_p()
+        n = len(offsets)
+        check(self._lib.nvrx_crc_create(n, _u64_array(offsets), _u64_array(nbytes), device, C.byref(self._h)), "nvrx_crc_create")
+        cnt = C.c_uint64()
+        check(self._lib.nvrx_crc_info(self._h, C.byref(cnt)), "nvrx_crc_info")
+        self.n_values = cnt.value
+
+    def run(self, dev_base: int, host_values: int, host_ready: int, ready_value: int, stream: int) -> None:
+        check(self._lib.nvrx_crc_run(self._h, dev_base, host_values, host_ready, ready_value, stream), "nvrx_crc_run")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.nvrx_crc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def finish_crcs(offsets: Sequence[int], nbytes: Sequence[int], values_ptr: int, n_values: int, host_base: int) -> List[int]:
+    """CPU only: crc32 of every extent from the GPU's partial values and the host copy of the buffer (``nvrx_crc_finish``)."""
+    n = len(offsets)
+    out = (C.c_uint32 * max(n, 1))()
+    check(
+        _cabi.lib().nvrx_crc_finish(n, _u64_array(offsets), _u64_array(nbytes), values_ptr, n_values, host_base, out),
+        "nvrx_crc_finish",
+    )
+    return [out[i] for i in range(n)]
+
+
+def gpu_crc_enabled() -> bool:
+    """Opt-in (``NVRX_B200_GPU_CRC=1``, with zero-copy persistence): record checksums of published checkpoints come from a
+    kernel over the staging buffer instead of being left zero (or summed by CPU threads with ``NVRX_B200_ZIP_CRC=1``)."""
+    return os.environ.get("NVRX_B200_GPU_CRC", "0") == "1"
+
+
 def stream_wait_event(stream: int, ev: Event) -> None:
     check(_cabi.lib().nvrx_stream_wait_event(stream, ev.handle), "nvrx_stream_wait_event")
 
@@ -437,6 +481,7 @@ class Snapshot:
     pack_start: Optional[Event] = None
     pack_stop: Optional[Event] = None
     released: bool = False
+    crc_info: Optional[dict] = None  # where the GPU's checksum values land in the slot (opt-in, see gpu_crc_enabled)
 
     def drained(self) -> bool:
         return self.slot.done_event.query()
@@ -470,6 +515,7 @@ class Snapshot:
             "layout": self.layout,
             "owner_pid": os.getpid(),
             "owner_base": self.slot.buf.data_ptr,  # where the trainer's views of the slot live (valid in fork children)
+            "crc": self.crc_info,
         }
 
     def release(self) -> None:
@@ -536,6 +582,7 @@ class SnapshotEngine:
         self._slot_gen = 0
         self.launches = 0  # kernels launched by this engine (pack + scatter)
         self.resident_restores = 0  # restores that read a published slot in place (no host copy)
+        self._aux: Optional[Stream] = None  # checksum kernels (created on first use)
         self._pid = os.getpid()  # forked writers inherit this object; only the creator may tear it down
 
     # ---- singletons per device ------------------------------------------------------------------
@@ -678,12 +725,22 @@ class SnapshotEngine:
             from .ptzip import slot_tail_room
 
             tail_room = slot_tail_room(len(cuda_tensors))
-        slot = self._acquire_slot(plan.staging_bytes + tail_room)
+        crc = None
+        need = plan.staging_bytes
+        if container and gpu_crc_enabled():
+            crc = getattr(plan, "_crc", None)
+            if crc is None:
+                crc = plan._crc = CrcPlan(plan.offsets, plan.packed_nbytes, self.device)
+            crc_off = -(-plan.staging_bytes // 64) * 64  # partial values, then the ready word, behind the payload
+            ready_off = crc_off + -(-4 * crc.n_values // 8) * 8
+            need = ready_off + 8
+        slot = self._acquire_slot(need + tail_room)
         if self._staging_free is not None:
             # the previous drain may still be reading staging: order the pack after it on the GPU
             stream_wait_event(stream, self._staging_free)
 
         start = stop = None
+        packed_ev = Event(self.device) if crc is not None else None
         base = slot.drained_total
         if self.timing:
             # separate launches so the pack kernel can be timed on its own (bench / profiling)
@@ -692,6 +749,8 @@ class SnapshotEngine:
             start.record(stream)
             plan.pack(staging.ptr, stream)
             stop.record(stream)
+            if packed_ev is not None:
+                packed_ev.record(stream)
             self._side.wait_event(stop)
             check(
                 self.lib.nvrx_drain(
@@ -705,13 +764,30 @@ class SnapshotEngine:
             check(
                 self.lib.nvrx_snapshot(
                     plan._h, staging.ptr, slot.buf.data_ptr, self.drain_chunk, slot.buf.progress_ptr, base, stream,
-                    self._side.handle, None, slot.done_event.handle,
+                    self._side.handle, packed_ev.handle if packed_ev is not None else None, slot.done_event.handle,
                 ),
                 "nvrx_snapshot",
             )
         self.launches += (-(-plan.staging_bytes // self.drain_chunk) if not self.timing else 1) if plan.n_tiles else 0
         slot.drained_total = base + plan.staging_bytes
         self._staging_free = slot.done_event
+        crc_info = None
+        if crc is not None:
+            # checksum kernel on a third stream, concurrent with the drain: reads staging once more, sends one 32-bit value per
+            # 64 KiB and finally the ready word (= this snapshot's progress target) to the slot
+            if self._aux is None:
+                self._aux = Stream(self.device)
+            self._aux.wait_event(packed_ev)
+            crc.run(staging.ptr, slot.buf.data_ptr + crc_off, slot.buf.data_ptr + ready_off, slot.drained_total, self._aux.handle)
+            self.launches += 1
+            crc_done = Event(self.device)
+            crc_done.record(self._aux.handle)
+            # staging is free for the next pack only when the drain AND the checksum kernel are through with it
+            self._side.wait_event(crc_done)
+            free_ev = Event(self.device)
+            free_ev.record(self._side.handle)
+            self._staging_free = free_ev
+            crc_info = {"offset": crc_off, "n_values": crc.n_values, "ready_offset": ready_off, "ready_value": slot.drained_total}
 
         layout = PackedLayout(
             shapes=[tuple(t.shape) for t in cuda_tensors],
@@ -724,7 +800,7 @@ class SnapshotEngine:
         )
         return Snapshot(
             engine=self, slot=slot, layout=layout, progress_target=slot.drained_total, passthrough=passthrough,
-            n_total=len(all_tensors), pack_start=start, pack_stop=stop,
+            n_total=len(all_tensors), pack_start=start, pack_stop=stop, crc_info=crc_info,
         )
 
     # ---- restore --------------------------------------------------------------------------------
@@ -836,6 +912,8 @@ class SnapshotEngine:
         if os.getpid() != self._pid:
             return
         for plan in self._plans.values():
+            if getattr(plan, "_crc", None) is not None:
+                plan._crc.close()
             plan.close()
         self._plans.clear()
         for s in self._slots:

@@ -44,6 +44,7 @@ def ranges_for(descs, held) -> List[Tuple[int, int, object]]:
     A forked writer also sees the trainer's mapping (tensor views were created there) at the trainer's address."""
     out = []
     for desc, hb in zip(descs, held):
+        hb.crc_info = desc.get("crc")  # where the GPU left checksum values for this snapshot, if it did
         out.append((hb.data_ptr, hb.capacity, hb))
         base = desc.get("owner_base")
         if base and base != hb.data_ptr and desc.get("owner_pid") in (os.getppid(), os.getpid()):
@@ -79,6 +80,23 @@ def zero_copy_enabled() -> bool:
     return os.environ.get("NVRX_B200_ZERO_COPY", "0") == "1"
 
 
+def _gpu_crcs(slot, info: dict, offsets, sizes) -> List[int]:
+    """Record checksums from the partial values a kernel left behind the payload (``nvrx_crc_run``): wait for the ready word
+    (CPU only, like the drain's progress word), then chain values and left-over bytes (``nvrx_crc_finish``)."""
+    import time
+
+    from .engine import finish_crcs
+    from .persist import DRAIN_TIMEOUT_MS
+
+    ready = C.c_uint64.from_address(slot.data_ptr + info["ready_offset"])
+    deadline = time.monotonic() + DRAIN_TIMEOUT_MS / 1e3
+    while ready.value != info["ready_value"]:
+        if time.monotonic() > deadline:
+            raise TimeoutError("checksum values of the snapshot did not arrive")
+        time.sleep(0.0002)
+    return finish_crcs(offsets, sizes, slot.data_ptr + info["offset"], info["n_values"], slot.data_ptr)
+
+
 def _try_link(obj, target: str, records, protocol) -> bool:
     """Publish the snapshot slot itself as the checkpoint file (``ptzip.publish_slot``) when every tensor of ``obj`` lives
     in ONE named slot, in storage order, at the container's offsets.  False = nothing published, copy instead."""
@@ -98,7 +116,10 @@ def _try_link(obj, target: str, records, protocol) -> bool:
     if slot is None:
         return False
     crcs = None
-    if os.environ.get("NVRX_B200_ZIP_CRC", "0") not in ("", "0"):
+    info = getattr(slot, "crc_info", None)
+    if info:
+        crcs = _gpu_crcs(slot, info, offsets, sizes)
+    elif os.environ.get("NVRX_B200_ZIP_CRC", "0") not in ("", "0"):
         crcs = [slot.crc32(off, nb, WRITE_THREADS) if nb else 0 for off, nb in zip(offsets, sizes)]
     small = ptzip.small_records(obj, protocol)
     return ptzip.publish_slot("/dev/shm" + slot.name, target, small, offsets, sizes, crcs=crcs)

@@ -2,7 +2,7 @@
 checkpoint file on /dev/shm (hard link), so a save is durable as soon as its drain has finished.
 
 The host half is covered on the CPU (tests/test_zero_copy_cpu.py).  These tests were written after round 1's GPU budget was
-spent and have not run on a B200 yet; they are skipped unless NVRX_B200_TEST_ZERO_COPY=1 so that an unvalidated opt-in mode
+spent and have not run on a B200 yet; they are skipped unless NVRX_B200_TEST_UNVALIDATED=1 so that an unvalidated opt-in mode
 cannot turn the default suite red.  Round 2: run them, then drop the gate."""
 import os
 
@@ -11,7 +11,7 @@ import torch
 
 pytestmark = [
     pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("NVRX_B200_TEST_ZERO_COPY") != "1", reason="opt-in mode, not yet validated on a B200"),
+    pytest.mark.skipif(os.environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="opt-in mode, not yet validated on a B200"),
 ]
 
 

@@ -3,6 +3,7 @@ torch.load-able file by a hard link.  The GPU's part (pack at the planner's expl
 in for by writing the oracle's bytes at the offsets the CUDA-free planner reports."""
 import os
 import zipfile
+import zlib
 
 import pytest
 import torch
@@ -204,3 +205,52 @@ def test_slot_choice_skips_published_checkpoints(built_library, shm_dir):
     finally:
         for s in slots:
             s.buf.close()
+
+
+def test_published_records_carry_the_gpus_checksums(built_library, shm_dir, monkeypatch):
+    """Writer half of the GPU CRC path: partial values (here: from the oracle) and the ready word sit behind the payload; the
+    published file must be a ZIP whose every record passes its CRC check, with no CPU checksum pass configured."""
+    import ctypes as C
+    import threading
+    import time
+
+    import numpy as np
+
+    from oracle import crc_oracle as co
+    from nvidia_resiliency_ext.checkpointing.b200.persist import save_snapshot_with_torch
+
+    monkeypatch.setenv("NVRX_B200_ZERO_COPY", "1")
+    monkeypatch.setenv("NVRX_B200_ZIP_CRC", "0")
+    state = _state()
+    name = f"/nvrx_zc_gpucrc_{os.getpid()}"
+    hb, desc, skeleton = _slot_with_snapshot(state, name, spare=1 << 16)
+    try:
+        lay = desc["layout"]
+        chunks = co.chunks_of(lay.offsets, lay.packed_nbytes)
+        payload = hb.as_tensor(hb.capacity).numpy()
+        values = np.array([co.chunk_value(payload[o : o + r * 512].tobytes()) for o, r, _ in chunks], dtype=np.uint32)
+        crc_off = -(-lay.total_bytes // 64) * 64
+        ready_off = crc_off + -(-4 * len(values) // 8) * 8
+        desc["crc"] = {"offset": crc_off, "n_values": len(values), "ready_offset": ready_off, "ready_value": 77}
+
+        def gpu():  # values and the ready word arrive a little after the payload, as from the checksum stream
+            time.sleep(0.2)
+            payload[crc_off : crc_off + 4 * len(values)] = values.view(np.uint8)
+            C.c_uint64.from_address(hb.data_ptr + ready_off).value = 77
+
+        t = threading.Thread(target=gpu)
+        t.start()
+        target = shm_dir / "ckpt.pt"
+        save_snapshot_with_torch(skeleton, str(target), desc)
+        t.join()
+        assert os.path.samefile("/dev/shm" + name, target)
+        _same(torch.load(target, weights_only=False), state)
+        with zipfile.ZipFile(target) as zf:
+            for n in zf.namelist():
+                if n != "archive/.pad":
+                    zf.read(n)  # raises BadZipFile on a wrong CRC
+            tensors = orc.flatten_tensors(state)
+            for i, t_ in enumerate(tensors):
+                assert zf.getinfo(f"archive/data/{i}").CRC == zlib.crc32(t_.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if t_.numel() else b"")
+    finally:
+        hb.close()
