@@ -16,14 +16,15 @@ cuobjdump -res-usage "$SO" | awk '/Function/ {name=$2} /REG:/ {gsub(":$","",name
 echo
 echo "## SASS mnemonic counts per kernel (cuobjdump -sass)"
 echo
-echo '| kernel | UBLKCP.S.G (TMA bulk g→s) | UBLKCP.G.S (TMA bulk s→g) | SYNCS (mbarrier) | LDG.E[.NA].128 | STG.E[.NA].128 | LDG.E[.NA].64 | STG.E[.NA].64 | SHFL | F2FP.BF16 (cvt.rn.bf16x2) |'
-echo '|---|---|---|---|---|---|---|---|---|---|'
+echo '| kernel | UBLKCP.S.G (TMA bulk g→s) | UBLKCP.G.S (TMA bulk s→g) | SYNCS (mbarrier) | LDG.E[.NA].128 | STG.E[.NA].128 | LDG.E[.NA].64 | STG.E[.NA].64 | SHFL | F2FP.BF16 (cvt.rn.bf16x2) | LDS (table lookups) |'
+echo '|---|---|---|---|---|---|---|---|---|---|---|'
 cuobjdump -sass "$SO" | awk '
-  /Function :/ { if (name != "") print name, a, b, c, d, e, f, g, h, i; name=$3; a=b=c=d=e=f=g=h=i=0 }
-  /UBLKCP\.S\.G/ {a++} /UBLKCP\.G\.S/ {b++} /SYNCS/ {c++} /LDG\.E(\.[A-Z]+)*\.128/ {d++} /STG\.E(\.[A-Z]+)*\.128/ {e++} /LDG\.E(\.[A-Z]+)*\.64/ {f++} /STG\.E(\.[A-Z]+)*\.64/ {g++} /SHFL/ {h++} /F2FP.*BF16/ {i++}
-  END { if (name != "") print name, a, b, c, d, e, f, g, h, i }' | while read -r name a b c d e f g h i; do
-    echo "| \`$(echo "$name" | c++filt | sed 's/(.*//')\` | $a | $b | $c | $d | $e | $f | $g | $h | $i |"; done
+  /Function :/ { if (name != "") print name, a, b, c, d, e, f, g, h, i, j; name=$3; a=b=c=d=e=f=g=h=i=j=0 }
+  /UBLKCP\.S\.G/ {a++} /UBLKCP\.G\.S/ {b++} /SYNCS/ {c++} /LDG\.E(\.[A-Z]+)*\.128/ {d++} /STG\.E(\.[A-Z]+)*\.128/ {e++} /LDG\.E(\.[A-Z]+)*\.64/ {f++} /STG\.E(\.[A-Z]+)*\.64/ {g++} /SHFL/ {h++} /F2FP.*BF16/ {i++} / LDS/ {j++}
+  END { if (name != "") print name, a, b, c, d, e, f, g, h, i, j }' | while read -r name a b c d e f g h i j; do
+    echo "| \`$(echo "$name" | c++filt | sed 's/(.*//')\` | $a | $b | $c | $d | $e | $f | $g | $h | $i | $j |"; done
 echo
 echo "Reading: \`walk_*<0>\` = pack (+ optional narrow), \`walk_*<1>\` = scatter (+ optional widen).  In the TMA walkers the bulk tiles move"
 echo "only through UBLKCP (no per-thread LDG/STG.128 in the tile loop); the remaining LDG/STG are the ragged-edge, narrow and"
-echo "widen paths.  \`.NA\` = no-allocate cache hint (streaming data is not kept in L1)."
+echo "widen paths.  \`.NA\` = no-allocate cache hint (streaming data is not kept in L1).  \`crc_chunks\` (opt-in checksum kernel):"
+echo "\`LDG.128\` row loads, \`LDS\` = lookups in the shared-memory operator tables, 64 \`SHFL\` = the unrolled chain over the lanes."
