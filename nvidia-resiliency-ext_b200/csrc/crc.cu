@@ -1,6 +1,7 @@
 // crc.cu -- host side of the GPU CRC-32 (tables, chunk enumeration, C ABI) and the CPU-only chaining of the partial values.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -188,13 +189,32 @@ int nvrx_crc_run(nvrx_crc* c, const void* dev_base, uint32_t* host_values, uint6
     uint32_t* tables = nullptr;
     int rc = device_tables(c->device, &tables);
     if (rc) return rc;
-    constexpr int kWarps = 8;
-    const uint64_t want = (n + kWarps - 1) / kWarps;
-    const uint32_t grid = static_cast<uint32_t>(want < static_cast<uint64_t>(c->sm_count) * 4 ? want : static_cast<uint64_t>(c->sm_count) * 4);
     unsigned long long* d_ready = reinterpret_cast<unsigned long long*>(c->d_vals + c->ready_index);
-    nvrx::crc_chunks<kWarps><<<grid ? grid : 1, kWarps * 32, 0, st>>>(static_cast<const uint8_t*>(dev_base), c->d_chunks,
-                                                                       static_cast<uint32_t>(n), tables, c->d_vals, d_ready,
-                                                                       static_cast<unsigned long long>(ready_value));
+    const uint8_t* src = static_cast<const uint8_t*>(dev_base);
+    const char* variant = getenv("NVRX_B200_CRC_VARIANT");  // "shared": one copy of the tables per CTA (A/B measurements)
+    if (variant && !strcmp(variant, "shared")) {
+        constexpr int kWarps = 8;
+        const uint64_t want = (n + kWarps - 1) / kWarps;
+        const uint64_t cap = static_cast<uint64_t>(c->sm_count) * 4;
+        const uint32_t grid = static_cast<uint32_t>(want < cap ? want : cap);
+        nvrx::crc_chunks<kWarps><<<grid ? grid : 1, kWarps * 32, 0, st>>>(src, c->d_chunks, static_cast<uint32_t>(n), tables,
+                                                                           c->d_vals, d_ready,
+                                                                           static_cast<unsigned long long>(ready_value));
+    } else {
+        // default: Z(512) replicated per lane in 128 KiB of shared memory, one 32-warp CTA per SM
+        constexpr int kWarps = 32;
+        static std::once_flag attr_once;
+        static cudaError_t attr_rc = cudaSuccess;
+        std::call_once(attr_once, [] {
+            attr_rc = cudaFuncSetAttribute(nvrx::crc_chunks_private<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(nvrx::kCrcPrivateSmemBytes));
+        });
+        NVRX_CUDA(attr_rc);
+        const uint64_t want = (n + kWarps - 1) / kWarps;
+        const uint32_t grid = static_cast<uint32_t>(want < static_cast<uint64_t>(c->sm_count) ? want : c->sm_count);
+        nvrx::crc_chunks_private<kWarps><<<grid ? grid : 1, kWarps * 32, nvrx::kCrcPrivateSmemBytes, st>>>(
+            src, c->d_chunks, static_cast<uint32_t>(n), tables, c->d_vals, d_ready, static_cast<unsigned long long>(ready_value));
+    }
     NVRX_CUDA(cudaGetLastError());
     if (n) NVRX_CUDA(cudaMemcpyAsync(host_values, c->d_vals, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (host_ready) NVRX_CUDA(cudaMemcpyAsync(host_ready, d_ready, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));

@@ -40,6 +40,22 @@ NVRX_HD uint32_t crc_apply(const uint32_t* op, uint32_t s) {
     return op[s & 0xffu] ^ op[256 + ((s >> 8) & 0xffu)] ^ op[512 + ((s >> 16) & 0xffu)] ^ op[768 + (s >> 24)];
 }
 
+// The same map through a table replicated per lane: entry e of lane l lives at op32[e * 32 + l], i.e. always in shared-memory
+// bank l -- 32 lanes looking up 32 unrelated entries never collide (a single copy serves random indices with ~3-way bank
+// conflicts, which is what bounds the plain kernel).
+NVRX_HD uint32_t crc_apply_lane(const uint32_t* op32, uint32_t lane, uint32_t s) {
+    return op32[((s & 0xffu) << 5) + lane] ^ op32[((256u + ((s >> 8) & 0xffu)) << 5) + lane] ^
+           op32[((512u + ((s >> 16) & 0xffu)) << 5) + lane] ^ op32[((768u + (s >> 24)) << 5) + lane];
+}
+
+NVRX_HD void crc_row_step_lane(const uint32_t* z512x32, uint32_t lane, uint32_t t[4], uint32_t w0, uint32_t w1, uint32_t w2,
+                               uint32_t w3) {
+    t[0] = crc_apply_lane(z512x32, lane, t[0]) ^ w0;
+    t[1] = crc_apply_lane(z512x32, lane, t[1]) ^ w1;
+    t[2] = crc_apply_lane(z512x32, lane, t[2]) ^ w2;
+    t[3] = crc_apply_lane(z512x32, lane, t[3]) ^ w3;
+}
+
 // One row step of a lane: four column values advance by one row each.
 NVRX_HD void crc_row_step(const uint32_t* z512, uint32_t t[4], uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     t[0] = crc_apply(z512, t[0]) ^ w0;
@@ -94,6 +110,51 @@ crc_chunks(const uint8_t* __restrict__ base, const CrcChunk* __restrict__ chunks
         for (; r < ch.rows; ++r) {
             const uint4 a = __ldg(p + r * 32);
             crc_row_step(z512, t, a.x, a.y, a.z, a.w);
+        }
+        const uint32_t u = crc_fold_lane(z4, t);
+        uint32_t s = 0;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) s = crc_chain_lane(z16, s, __shfl_sync(0xffffffffu, u, l));
+        if (lane == 0) out[c] = s;
+    }
+}
+
+// Same algorithm with the hot operator Z(512) replicated per lane in 128 KiB of dynamic shared memory (one CTA per SM).
+// With conflict-free lookups the kernel is bound by the LDG stream, i.e. by HBM, instead of by shared-memory replays.
+constexpr uint32_t kCrcPrivateSmemBytes = kCrcOpWords * 32 * sizeof(uint32_t);
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+crc_chunks_private(const uint8_t* __restrict__ base, const CrcChunk* __restrict__ chunks, uint32_t n_chunks,
+                   const uint32_t* __restrict__ tables, uint32_t* __restrict__ out, unsigned long long* ready_word,
+                   unsigned long long ready_value) {
+    extern __shared__ uint32_t s_z512x32[];  // [entry][lane]
+    __shared__ uint32_t s_small[2 * kCrcOpWords];  // Z4 | Z16, single copies (used 4 + 32 times per chunk)
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ready_word = ready_value;
+    for (uint32_t i = threadIdx.x; i < kCrcOpWords * 32; i += WARPS * 32) s_z512x32[i] = tables[i >> 5];
+    for (uint32_t i = threadIdx.x; i < 2 * kCrcOpWords; i += WARPS * 32) s_small[i] = tables[kCrcOpWords + i];
+    __syncthreads();
+    const uint32_t* z4 = s_small;
+    const uint32_t* z16 = s_small + kCrcOpWords;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    const uint32_t n_warps = gridDim.x * WARPS;
+    for (uint32_t c = warp; c < n_chunks; c += n_warps) {
+        const CrcChunk ch = chunks[c];
+        const uint4* p = reinterpret_cast<const uint4*>(base + ch.off) + lane;
+        uint32_t t[4] = {0u, 0u, 0u, 0u};
+        uint32_t r = 0;
+        for (; r + 4 <= ch.rows; r += 4) {
+            const uint4 a = __ldg(p + (r + 0) * 32), b = __ldg(p + (r + 1) * 32);
+            const uint4 d = __ldg(p + (r + 2) * 32), e = __ldg(p + (r + 3) * 32);
+            crc_row_step_lane(s_z512x32, lane, t, a.x, a.y, a.z, a.w);
+            crc_row_step_lane(s_z512x32, lane, t, b.x, b.y, b.z, b.w);
+            crc_row_step_lane(s_z512x32, lane, t, d.x, d.y, d.z, d.w);
+            crc_row_step_lane(s_z512x32, lane, t, e.x, e.y, e.z, e.w);
+        }
+        for (; r < ch.rows; ++r) {
+            const uint4 a = __ldg(p + r * 32);
+            crc_row_step_lane(s_z512x32, lane, t, a.x, a.y, a.z, a.w);
         }
         const uint32_t u = crc_fold_lane(z4, t);
         uint32_t s = 0;

@@ -25,3 +25,21 @@ extern "C" int crc_lanes_chunk_value(const uint8_t* chunk, uint32_t rows, const 
     *out = s;
     return 0;
 }
+
+// Same walk through the lane-replicated table of crc_chunks_private<> (entry e of lane l at z512x32[e * 32 + l]).
+extern "C" int crc_lanes_chunk_value_private(const uint8_t* chunk, uint32_t rows, const uint32_t* z512x32, const uint32_t* z4,
+                                             const uint32_t* z16, uint32_t* out) {
+    if (!chunk || !rows || rows > nvrx::kCrcChunkRows || !out) return 1;
+    uint32_t t[32][4];
+    memset(t, 0, sizeof(t));
+    for (uint32_t r = 0; r < rows; ++r)
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            uint32_t w[4];
+            memcpy(w, chunk + static_cast<uint64_t>(r) * nvrx::kCrcRowBytes + lane * 16, 16);
+            nvrx::crc_row_step_lane(z512x32, lane, t[lane], w[0], w[1], w[2], w[3]);
+        }
+    uint32_t s = 0;
+    for (uint32_t lane = 0; lane < 32; ++lane) s = nvrx::crc_chain_lane(z16, s, nvrx::crc_fold_lane(z4, t[lane]));
+    *out = s;
+    return 0;
+}

@@ -19,7 +19,9 @@ def lanes():
     assert res.returncode == 0, res.stdout + res.stderr
     lib = C.CDLL(str(ROOT / "oracle" / "_build" / "libcrc_lanes.so"))
     lib.crc_lanes_chunk_value.restype = C.c_int
-    lib.crc_lanes_chunk_value.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+    for fn in (lib.crc_lanes_chunk_value, lib.crc_lanes_chunk_value_private):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     return lib
 
 
@@ -48,6 +50,11 @@ def test_lane_arithmetic_gives_the_chunk_value(built_library, lanes):
         out = C.c_uint32()
         rc = lanes.crc_lanes_chunk_value(data.ctypes.data, rows, z512.ctypes.data, z4.ctypes.data, z16.ctypes.data, C.byref(out))
         assert rc == 0 and out.value == co.chunk_value(data.tobytes()), rows
+        # the default kernel's table layout: one copy of Z(512) per lane, entry-major
+        z512x32 = np.repeat(z512, 32)
+        out2 = C.c_uint32()
+        rc = lanes.crc_lanes_chunk_value_private(data.ctypes.data, rows, z512x32.ctypes.data, z4.ctypes.data, z16.ctypes.data, C.byref(out2))
+        assert rc == 0 and out2.value == out.value, rows
 
 
 def finish(offsets, nbytes, values, payload):
