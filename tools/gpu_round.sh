@@ -38,6 +38,8 @@ if [[ $WHAT == zerocopy ]]; then
   # opt-in modes written without GPU time in round 1: zero-copy persistence and the DCP async writer.  Validate, then measure.
   NVRX_B200_TEST_UNVALIDATED=1 guarded timeout 900 python -m pytest tests/test_gpu_zcrc.py tests/test_gpu_zzero_copy.py tests/test_gpu_zdcp.py -m gpu -q --timeout=600 > gpurun_out/pytest_zerocopy.log 2>&1
   tail -25 gpurun_out/pytest_zerocopy.log
+  guarded timeout 600 python tools/crc_bench.py --gb 2 > gpurun_out/crc_bench.jsonl 2> gpurun_out/crc_bench.err
+  guarded timeout 600 python tools/crc_bench.py --gb 16 >> gpurun_out/crc_bench.jsonl 2>> gpurun_out/crc_bench.err; cat gpurun_out/crc_bench.jsonl
   guarded timeout 900 python bench.py > gpurun_out/bench_copy.json 2> gpurun_out/bench_copy.err; cat gpurun_out/bench_copy.json
   NVRX_B200_ZERO_COPY=1 NVRX_B200_GPU_CRC=1 guarded timeout 900 python bench.py > gpurun_out/bench_zerocopy.json 2> gpurun_out/bench_zerocopy.err; tail -3 gpurun_out/bench_zerocopy.err; cat gpurun_out/bench_zerocopy.json
 fi
