@@ -281,8 +281,8 @@ def finish_crcs(offsets: Sequence[int], nbytes: Sequence[int], values_ptr: int, 
 
 
 def gpu_crc_enabled() -> bool:
-    """Opt-in (``NVRX_B200_GPU_CRC=1``, with zero-copy persistence): record checksums of published checkpoints come from a
-    kernel over the staging buffer instead of being left zero (or summed by CPU threads with ``NVRX_B200_ZIP_CRC=1``)."""
+    """Opt-in (``NVRX_B200_GPU_CRC=1``): record checksums of checkpoint files come from a kernel over the staging buffer
+    instead of being left zero (or summed by CPU threads with ``NVRX_B200_ZIP_CRC=1``)."""
     return os.environ.get("NVRX_B200_GPU_CRC", "0") == "1"
 
 
@@ -727,7 +727,7 @@ class SnapshotEngine:
             tail_room = slot_tail_room(len(cuda_tensors))
         crc = None
         need = plan.staging_bytes
-        if container and gpu_crc_enabled():
+        if gpu_crc_enabled() and not passthrough and len(cuda_tensors) > 0:
             crc = getattr(plan, "_crc", None)
             if crc is None:
                 crc = plan._crc = CrcPlan(plan.offsets, plan.packed_nbytes, self.device)

@@ -97,22 +97,34 @@ def _gpu_crcs(slot, info: dict, offsets, sizes) -> List[int]:
     return finish_crcs(offsets, sizes, slot.data_ptr + info["offset"], info["n_values"], slot.data_ptr)
 
 
-def _try_link(obj, target: str, records, protocol) -> bool:
-    """Publish the snapshot slot itself as the checkpoint file (``ptzip.publish_slot``) when every tensor of ``obj`` lives
-    in ONE named slot, in storage order, at the container's offsets.  False = nothing published, copy instead."""
-    from . import ptzip
+def _locate_or_none(ptr: int, nbytes: int):
+    hb, off = _locate(ptr, nbytes)
+    return None if hb is None else (hb, off)
 
+
+def _single_slot(records):
+    """``(slot, offsets, sizes)`` when the storages of the object are ``data/0..n-1`` and every non-empty one lives in ONE named
+    snapshot slot; else ``(None, [], [])``."""
     if [r[0] for r in records] != [f"data/{i}" for i in range(len(records))]:
-        return False
+        return None, [], []
     slot, offsets, sizes = None, [], []
     for _, ptr, nbytes in records:
         hb, off = _locate(ptr, nbytes) if nbytes else (slot, 0)
         if nbytes:
             if hb is None or not hb.name or (slot is not None and hb.name != slot.name):
-                return False
+                return None, [], []
             slot = hb
         offsets.append(off)
         sizes.append(nbytes)
+    return slot, offsets, sizes
+
+
+def _try_link(obj, target: str, records, protocol) -> bool:
+    """Publish the snapshot slot itself as the checkpoint file (``ptzip.publish_slot``) when every tensor of ``obj`` lives
+    in ONE named slot, in storage order, at the container's offsets.  False = nothing published, copy instead."""
+    from . import ptzip
+
+    slot, offsets, sizes = _single_slot(records)
     if slot is None:
         return False
     crcs = None
@@ -122,7 +134,8 @@ def _try_link(obj, target: str, records, protocol) -> bool:
     elif os.environ.get("NVRX_B200_ZIP_CRC", "0") not in ("", "0"):
         crcs = [slot.crc32(off, nb, WRITE_THREADS) if nb else 0 for off, nb in zip(offsets, sizes)]
     small = ptzip.small_records(obj, protocol)
-    return ptzip.publish_slot("/dev/shm" + slot.name, target, small, offsets, sizes, crcs=crcs)
+    keep = info["ready_offset"] + 8 if info else 0  # the values stay readable in the published file's pad area
+    return ptzip.publish_slot("/dev/shm" + slot.name, target, small, offsets, sizes, crcs=crcs, keep_until=keep)
 
 
 def save(obj, f, *args, **kwargs) -> str:
@@ -147,6 +160,16 @@ def save(obj, f, *args, **kwargs) -> str:
         # a file object was opened (exclusively, by the managers) on its name: the link replaces that empty file
         if isinstance(target, str) and _try_link(obj, target, records, protocol):
             return "linked"
+    if is_path:
+        # the GPU summed the records while the snapshot drained (opt-in): write our own payload-first container, whose headers
+        # take those checksums -- PyTorch's writer would either leave them zero or sum 16 GB on one core
+        slot, offsets, sizes = _single_slot(records)
+        info = getattr(slot, "crc_info", None) if slot is not None else None
+        if info and protocol == torch.serialization.DEFAULT_PROTOCOL:
+            from . import ptzip
+
+            ptzip.save(obj, f, locate=_locate_or_none, threads=WRITE_THREADS, crcs=_gpu_crcs(slot, info, offsets, sizes))
+            return "parallel+gpu-crc"
     with torch.serialization.skip_data():
         torch.save(obj, f, **kwargs)
     if not is_path:

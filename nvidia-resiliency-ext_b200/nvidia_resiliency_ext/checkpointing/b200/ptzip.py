@@ -251,9 +251,11 @@ def write_container(
 
 
 def save(obj: Any, path, *, locate: Callable[[int, int], Optional[Tuple[Any, int]]], threads: int = 16,
-         compute_crc: bool = True, file_size: Optional[int] = None, force_zip64: bool = False) -> PayloadLayout:
+         compute_crc: bool = True, file_size: Optional[int] = None, force_zip64: bool = False,
+         crcs: Optional[Sequence[int]] = None) -> PayloadLayout:
     """Write ``obj`` as a checkpoint with the payload-first layout.  ``locate(data_ptr, nbytes)`` maps a storage to
-    ``(HostBuffer, offset)`` (payload copied by the buffer's parallel writer) or ``None`` (copied from process memory)."""
+    ``(HostBuffer, offset)`` (payload copied by the buffer's parallel writer) or ``None`` (copied from process memory).
+    ``crcs``: record checksums that are already known (one per storage, e.g. from the GPU) -- nothing is summed here then."""
     import ctypes as C
 
     small, storages = describe(obj)
@@ -263,6 +265,9 @@ def save(obj: Any, path, *, locate: Callable[[int, int], Optional[Tuple[Any, int
     try:
         total = file_size if file_size is not None else layout.end + tail_size(archive, small, len(storages), force_zip64)
         os.ftruncate(fd, total)
+        known = list(crcs) if crcs is not None else None
+        assert known is None or len(known) == len(storages)
+        compute_crc = compute_crc and known is None
         crcs, by_buf = [], {}
         for rec, (ptr, nb) in zip(layout.records, storages):
             hit = locate(ptr, nb) if nb else None
@@ -279,7 +284,7 @@ def save(obj: Any, path, *, locate: Callable[[int, int], Optional[Tuple[Any, int
                 crcs.append(hb.crc32(off, nb, threads) if compute_crc else 0)
         for hb, offs, sizes, file_offs in by_buf.values():
             hb.writev_fd(offs, sizes, file_offs, fd, threads)
-        end = write_container(fd, layout, small, file_size=file_size, crcs=crcs, force_zip64=force_zip64)
+        end = write_container(fd, layout, small, file_size=file_size, crcs=known if known is not None else crcs, force_zip64=force_zip64)
         if file_size is None:
             os.ftruncate(fd, end)
     finally:
@@ -323,8 +328,12 @@ def publish_slot(
     sizes: Sequence[int],
     *,
     crcs: Optional[Sequence[int]] = None,
+    keep_until: int = 0,
 ) -> bool:
     """Turn the slot file ``slot_path`` into the checkpoint ``target`` without copying its payload.
+
+    ``keep_until``: payload-relative end of a region behind the storages that must stay intact (the GPU's checksum values);
+    the small records start after it.
 
     ``offsets[i]`` / ``sizes[i]``: where storage ``i`` sits in the payload region.  Returns False (nothing changed that
     matters: only bytes outside the storages are written) when the geometry is not the container's, the tail does not
@@ -333,6 +342,7 @@ def publish_slot(
     for rec, off, size in zip(lay.records, offsets, sizes):
         if size and off != rec.data_off - SLOT_PREFIX:
             return False
+    lay.end = max(lay.end, SLOT_PREFIX + keep_until)
     try:
         fd = os.open(slot_path, os.O_RDWR)
     except OSError:

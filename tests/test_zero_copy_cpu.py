@@ -244,13 +244,26 @@ def test_published_records_carry_the_gpus_checksums(built_library, shm_dir, monk
         save_snapshot_with_torch(skeleton, str(target), desc)
         t.join()
         assert os.path.samefile("/dev/shm" + name, target)
+        # without the hard link (zero-copy off, or another file system) the same checksums go into a copied container
+        monkeypatch.setenv("NVRX_B200_ZERO_COPY", "0")
+        copied = shm_dir / "copied.pt"
+        save_snapshot_with_torch(skeleton, str(copied), desc)
+        assert not os.path.samefile("/dev/shm" + name, copied) and os.stat(copied).st_nlink == 1
+        for path in (target, copied):
+            _check_archive(path, state)
+    finally:
+        hb.close()
+
+
+def _check_archive(target, state):
+    if True:
         _same(torch.load(target, weights_only=False), state)
+        _same(torch.load(target, weights_only=False, mmap=True), state)
+        archive = "archive" if os.stat(target).st_nlink > 1 else os.path.splitext(os.path.basename(target))[0]
         with zipfile.ZipFile(target) as zf:
             for n in zf.namelist():
-                if n != "archive/.pad":
+                if not n.endswith("/.pad"):
                     zf.read(n)  # raises BadZipFile on a wrong CRC
             tensors = orc.flatten_tensors(state)
             for i, t_ in enumerate(tensors):
-                assert zf.getinfo(f"archive/data/{i}").CRC == zlib.crc32(t_.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if t_.numel() else b"")
-    finally:
-        hb.close()
+                assert zf.getinfo(f"{archive}/data/{i}").CRC == zlib.crc32(t_.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if t_.numel() else b"")
