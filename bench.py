@@ -304,7 +304,13 @@ def run_engine(args, rank, world, local):
         resident = None
         if os.environ.get("NVRX_B200_ZERO_COPY") == "1":  # opt-in: the file is a hard link to a slot that is still pinned
             resident = engine.resident_source(path, lt)
-        back = engine.restore(lt, widen_to=widen if args.narrow else None, resident=resident)
+        file_source = None
+        if resident is None and os.environ.get("NVRX_B200_RESTORE_PREAD") == "1":  # opt-in A/B: pread instead of mmap gather
+            from nvidia_resiliency_ext.checkpointing.b200.ptzip import tensor_offsets_in_file
+
+            offs = tensor_offsets_in_file(path, lt)
+            file_source = (str(path), offs) if offs is not None else None
+        back = engine.restore(lt, widen_to=widen if args.narrow else None, resident=resident, file_source=file_source)
         torch.cuda.synchronize()
         restore_s = max_over_ranks(time.perf_counter() - t0)
         launches += 1

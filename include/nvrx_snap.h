@@ -207,6 +207,10 @@ int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets,
  * per-tensor H2D copies of local/basic_state_dict.py:184-187). */
 int nvrx_hostbuf_gather(nvrx_hostbuf* hb, int64_t n, const void* const* srcs, const uint64_t* nbytes,
                         const uint64_t* dst_offsets, int threads);
+/* Restore-side alternative to gather when the tensors come from a file: n file ranges -> payload offsets with `threads`
+ * pread workers (no page-by-page faulting of an mmap of the file). */
+int nvrx_hostbuf_readv_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, const uint64_t* nbytes, const uint64_t* file_offs,
+                          int fd, int threads);
 /* crc32 (zlib polynomial) of a payload range computed with `threads` workers and combined. */
 int nvrx_hostbuf_crc32(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int threads, uint32_t* out);
 

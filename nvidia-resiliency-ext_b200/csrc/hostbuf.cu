@@ -424,6 +424,54 @@ int nvrx_hostbuf_write_fd(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int
     return nvrx_hostbuf_writev_fd(hb, 1, &offset, &bytes, &file_off, fd, threads);
 }
 
+// Mirror of writev_fd for restore: file ranges -> payload with `threads` pread workers.  Reading through the page cache copies
+// without faulting the source in page by page, which is what bounds a memcpy from an mmap of the checkpoint file.
+int nvrx_hostbuf_readv_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, const uint64_t* nbytes, const uint64_t* file_offs,
+                          int fd, int threads) {
+    if (!hb || fd < 0 || n < 0 || (n > 0 && (!offsets || !nbytes || !file_offs))) return NVRX_E_INVALID;
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets[i] > hb->capacity || nbytes[i] > hb->capacity - offsets[i]) return NVRX_E_INVALID;
+    if (threads < 1) threads = 1;
+    uint8_t* base = hb->map + kHeaderBytes;
+    const uint64_t grain = 8ull << 20;
+    std::vector<uint64_t> first_piece(static_cast<size_t>(n) + 1, 0);
+    for (int64_t i = 0; i < n; ++i) first_piece[i + 1] = first_piece[i] + (nbytes[i] + grain - 1) / grain;
+    const uint64_t total_pieces = first_piece[n];
+    if (total_pieces == 0) return NVRX_OK;
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> err{0};
+    auto worker = [&] {
+        int64_t ext = 0;
+        while (!err.load(std::memory_order_relaxed)) {
+            const uint64_t piece = next.fetch_add(1);
+            if (piece >= total_pieces) break;
+            while (first_piece[ext + 1] <= piece) ++ext;
+            const uint64_t o = (piece - first_piece[ext]) * grain;
+            const uint64_t len = std::min<uint64_t>(grain, nbytes[ext] - o);
+            uint64_t done = 0;
+            while (done < len) {
+                ssize_t r = pread(fd, base + offsets[ext] + o + done, len - done, static_cast<off_t>(file_offs[ext] + o + done));
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) {  // error, or the file is shorter than the caller said
+                    err.store(r < 0 && errno ? errno : EIO);
+                    return;
+                }
+                done += static_cast<uint64_t>(r);
+            }
+        }
+    };
+    const int nthreads = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(threads), total_pieces));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    if (err.load()) {
+        errno = err.load();
+        return NVRX_E_SYS;
+    }
+    return NVRX_OK;
+}
+
 int nvrx_hostbuf_gather(nvrx_hostbuf* hb, int64_t n, const void* const* srcs, const uint64_t* nbytes, const uint64_t* dst_offsets,
                         int threads) {
     if (!hb || n < 0 || (n > 0 && (!srcs || !nbytes || !dst_offsets))) return NVRX_E_INVALID;

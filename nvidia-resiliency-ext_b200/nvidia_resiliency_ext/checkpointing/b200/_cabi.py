@@ -76,6 +76,7 @@ EXPORTED_SYMBOLS = (
     "nvrx_hostbuf_write_fd",
     "nvrx_hostbuf_writev_fd",
     "nvrx_hostbuf_gather",
+    "nvrx_hostbuf_readv_fd",
     "nvrx_hostbuf_crc32",
     "nvrx_crc_create",
     "nvrx_crc_destroy",
@@ -163,6 +164,7 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_hostbuf_write_fd": (_int, [_vp, _u64, _u64, _int, _u64, _int]),
         "nvrx_hostbuf_writev_fd": (_int, [_vp, _i64, P(_u64), P(_u64), P(_u64), _int, _int]),
         "nvrx_hostbuf_gather": (_int, [_vp, _i64, P(_vp), P(_u64), P(_u64), _int]),
+        "nvrx_hostbuf_readv_fd": (_int, [_vp, _i64, P(_u64), P(_u64), P(_u64), _int, _int]),
         "nvrx_hostbuf_crc32": (_int, [_vp, _u64, _u64, _int, P(_u32)]),
         "nvrx_crc_create": (_int, [_i64, P(_u64), P(_u64), _int, P(_vp)]),
         "nvrx_crc_destroy": (_int, [_vp]),

@@ -362,6 +362,13 @@ class HostBuffer:
             "nvrx_hostbuf_writev_fd",
         )
 
+    def readv_fd(self, offsets: Sequence[int], nbytes: Sequence[int], file_offs: Sequence[int], fd: int, threads: int = 16) -> None:
+        n = len(offsets)
+        check(
+            self._lib.nvrx_hostbuf_readv_fd(self._h, n, _u64_array(offsets), _u64_array(nbytes), _u64_array(file_offs), fd, threads),
+            "nvrx_hostbuf_readv_fd",
+        )
+
     def gather(self, src_ptrs: Sequence[int], nbytes: Sequence[int], dst_offsets: Sequence[int], threads: int = 16) -> None:
         check(
             self._lib.nvrx_hostbuf_gather(self._h, len(src_ptrs), _ptr_array(src_ptrs), _u64_array(nbytes), _u64_array(dst_offsets), threads),
@@ -811,13 +818,16 @@ class SnapshotEngine:
         widen_to: Optional[Sequence[torch.dtype]] = None,
         out: Optional[Sequence[torch.Tensor]] = None,
         resident: Optional[Tuple[_Slot, Sequence[int]]] = None,
+        file_source: Optional[Tuple[str, Sequence[int]]] = None,
     ) -> List[torch.Tensor]:
         """CPU tensors -> CUDA tensors of this device with one H2D copy and one scatter kernel.
 
         ``widen_to[i] == torch.float32`` for a bf16 host tensor widens it in the scatter kernel (exact).
         ``resident`` (from :meth:`resident_source`): the tensors' bytes already sit in that pinned slot at those payload
         offsets (the checkpoint file is a hard link to the slot), so the gather into a pinned buffer is skipped and the
-        H2D reads the slot directly."""
+        H2D reads the slot directly.
+        ``file_source = (path, file offsets)`` (from ``ptzip.tensor_offsets_in_file``): fill the pinned slot with parallel
+        ``pread`` from the checkpoint file instead of a memcpy from the tensors' mmap (no page-by-page faults)."""
         host_tensors = [t.detach() for t in host_tensors]
         target_dtypes = [
             (widen_to[i] if widen_to is not None and widen_to[i] is not None else t.dtype)
@@ -842,7 +852,15 @@ class SnapshotEngine:
             slot = self._acquire_slot(plan.staging_bytes)
         staging = self._ensure_staging(plan.staging_bytes)
         try:
-            if resident is None:
+            if resident is None and file_source is not None:
+                path, file_offs = file_source
+                live = [(off, nb, fo) for off, nb, fo in zip(plan.offsets, plan.packed_nbytes, file_offs) if nb]
+                fd = os.open(path, os.O_RDONLY)
+                try:
+                    slot.buf.readv_fd([x[0] for x in live], [x[1] for x in live], [x[2] for x in live], fd, threads=self.prefault_threads or 8)
+                finally:
+                    os.close(fd)
+            elif resident is None:
                 # gather the CPU tensors into the pinned slot at the plan's offsets (no-op cost when the
                 # tensors already are views of one packed buffer with this layout)
                 srcs = [t if t.is_contiguous() else t.contiguous() for t in host_tensors]

@@ -10,6 +10,7 @@ by either implementation load with the other.  What differs is how the payload m
   scatter kernel.
 """
 
+import os
 from typing import Optional, Union
 
 import torch
@@ -145,6 +146,15 @@ class BasicTensorAwareStateDict(TensorAwareStateDict):
         # set by LocalCheckpointManager._load in zero-copy mode: the file may be a hard link to a slot that is still pinned in
         # this process (in-process restart), in which case the H2D reads the slot and nothing is copied on the host
         source = self.__dict__.pop("_b200_loaded_from", None)
-        resident = engine.resident_source(source, host) if source is not None and len(host) == len(current) else None
-        moved = iter(engine.restore(host, widen_to=widen_to, resident=resident))
+        resident = file_source = None
+        if source is not None and len(host) == len(current):
+            from ..b200 import fastsave, ptzip
+
+            if fastsave.zero_copy_enabled():
+                resident = engine.resident_source(source, host)
+            if resident is None and os.environ.get("NVRX_B200_RESTORE_PREAD", "0") == "1":
+                # opt-in (to be measured): fill the pinned slot by parallel pread from the file instead of from its mmap
+                offs = ptzip.tensor_offsets_in_file(source, host)
+                file_source = (source, offs) if offs is not None else None
+        moved = iter(engine.restore(host, widen_to=widen_to, resident=resident, file_source=file_source))
         self._replace_tensors([t if t.is_cuda else next(moved) for t in current])

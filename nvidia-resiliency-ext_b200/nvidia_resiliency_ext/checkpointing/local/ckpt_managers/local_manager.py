@@ -93,7 +93,7 @@ class LocalCheckpointManager(BaseCheckpointManager):
                 # map the file instead of copying it: tensors are read once more anyway (parallel gather into the
                 # pinned slot, then one H2D + scatter kernel)
                 loaded = torch.load(path, weights_only=False, mmap=True)  # nosec B614 - files are produced by this manager
-                if fastsave.zero_copy_enabled() and hasattr(loaded, "__dict__"):
+                if hasattr(loaded, "__dict__"):
                     loaded.__dict__["_b200_loaded_from"] = str(path)  # consumed by restore_tensor_device
                 return loaded
             except (RuntimeError, ValueError):

@@ -203,3 +203,32 @@ def test_persistent_writer_keeps_slots_mapped(built_library, tmp_path, monkeypat
     assert torch.equal(torch.load(tmp_path / "c2.pt")["a"], a2)
     persist._slot_cache.pop(name2).close(unlink=False)
     hb2.close()
+
+
+def test_readv_fd_fills_the_slot_from_a_file(built_library, tmp_path):
+    """Restore-side mirror of writev_fd: file ranges land at the given payload offsets (parallel pread)."""
+    from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
+
+    rng = np.random.default_rng(11)
+    blob = rng.integers(0, 256, 40_000_000, dtype=np.uint8)
+    path = tmp_path / "blob.bin"
+    blob.tofile(path)
+    hb = make_hb(48 << 20)
+    try:
+        file_offs = [0, 1_000_003, 17_000_000, 39_999_990]
+        sizes = [1_000_000, 15_999_997, 20_000_000, 10]
+        dst = [512, 2 << 20, 20 << 20, 47 << 20]
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            hb.readv_fd(dst, sizes, file_offs, fd, threads=5)
+            got = hb.as_tensor(hb.capacity).numpy()
+            for d, n, f in zip(dst, sizes, file_offs):
+                assert np.array_equal(got[d : d + n], blob[f : f + n])
+            with pytest.raises(SnapError):  # range beyond the end of the file
+                hb.readv_fd([0], [100], [39_999_990], fd, threads=2)
+            with pytest.raises(SnapError):  # destination outside the slot
+                hb.readv_fd([hb.capacity - 5], [100], [0], fd, threads=2)
+        finally:
+            os.close(fd)
+    finally:
+        hb.close()
