@@ -88,3 +88,18 @@ def test_local_manager_zero_copy_roundtrip(shm_dir, dist_1rank, built_library, m
         assert engine.resident_restores == before + 3
     finally:
         q.close()
+
+
+def test_restore_through_pread(tmp_path, shm_dir, dist_1rank, built_library, monkeypatch):
+    """NVRX_B200_RESTORE_PREAD=1: the pinned slot is filled by parallel pread from the file (any file system), then the usual
+    one H2D + one scatter kernel."""
+    from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+    monkeypatch.setenv("NVRX_B200_RESTORE_PREAD", "1")
+    for root in (tmp_path / "disk", shm_dir / "ram"):
+        mgr = LocalCheckpointManager(root)
+        mgr.save(BasicTensorAwareStateDict(_state(55)), 4, is_async=False)
+        assert mgr.find_latest() == 4
+        loaded, _ = mgr.load()
+        assert _equal(loaded.state_dict, _state(55)) and all(t.is_cuda for t in loaded.tensors)
