@@ -629,6 +629,7 @@ class SnapshotEngine:
             if retire:
                 # the pool is full of checkpoints somebody keeps: give this one up (the file keeps the pages, this process
                 # drops its mapping and pinning) and start a fresh buffer in its place
+                slot.__dict__.pop("_exchange_views", None)
                 slot.buf.close()
                 slot.buf = None
         if slot is None and len(self._slots) < self.max_host_slots:
@@ -644,6 +645,7 @@ class SnapshotEngine:
                 "(or raise NVRX_B200_MAX_HOST_SLOTS)",
             )
         if slot.buf is None or slot.buf.capacity < nbytes:
+            slot.__dict__.pop("_exchange_views", None)  # cached host views of the old buffer (b200/exchange.py)
             if slot.buf is not None:
                 slot.buf.close()
             self._slot_gen += 1
@@ -923,6 +925,7 @@ class SnapshotEngine:
             if not s.busy and s.buf is not None:
                 if s.done_event is not None:
                     s.done_event.synchronize()
+                s.__dict__.pop("_exchange_views", None)
                 s.buf.close()
                 s.buf = None
 

@@ -140,6 +140,42 @@ def _clique_barrier(engine: SnapshotEngine, group) -> None:
     dist.all_reduce(tok, group=group.group)
 
 
+def _geometry(group, all_placeholders, align: int, world: int) -> dict:
+    """Per-member layouts inside the exchange buffer, as PackedLayouts and as one union layout; cached on the group for as
+    long as the gathered placeholder lists are the same object."""
+    cached = group.__dict__.get("_packed_geometry")
+    if cached is not None and cached["key"] is all_placeholders and cached["align"] == align and cached["world"] == world:
+        return cached
+    layouts = []
+    for tps in all_placeholders:
+        offs, packed, total = expected_layout([tp.nbytes for tp in tps], [False] * len(tps), align)
+        layouts.append((offs, packed, total))
+    slot_bytes = max(total for _, _, total in layouts)
+    slot_bytes = (slot_bytes + 511) // 512 * 512
+    dev_lists = []
+    for r, (tps, (offs, packed, _)) in enumerate(zip(all_placeholders, layouts)):
+        names = [dtype_name(tp.hollow_tensor.dtype) for tp in tps]
+        dev_lists.append(
+            PackedLayout(
+                shapes=[tuple(tp.hollow_tensor.shape) for tp in tps], dtypes=names, src_dtypes=list(names),
+                offsets=[r * slot_bytes + o for o in offs], packed_nbytes=list(packed), total_bytes=world * slot_bytes, align=align,
+            )
+        )
+    union = PackedLayout(
+        shapes=[s for lay in dev_lists for s in lay.shapes],
+        dtypes=[d for lay in dev_lists for d in lay.dtypes],
+        src_dtypes=[d for lay in dev_lists for d in lay.src_dtypes],
+        offsets=[o for lay in dev_lists for o in lay.offsets],
+        packed_nbytes=[n for lay in dev_lists for n in lay.packed_nbytes],
+        total_bytes=world * slot_bytes,
+        align=align,
+    )
+    geo = {"key": all_placeholders, "align": align, "world": world, "layouts": layouts, "slot_bytes": slot_bytes,
+           "dev_lists": dev_lists, "union": union}
+    group.__dict__["_packed_geometry"] = geo
+    return geo
+
+
 def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders, target_device):
     """See module docstring.  ``all_placeholders[r]`` describes rank r's tensors (already all-gathered).
 
@@ -150,12 +186,10 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
     world, me = group.world_size, group.my_group_rank
     align = engine.align
 
-    layouts = []
-    for tps in all_placeholders:
-        offs, packed, total = expected_layout([tp.nbytes for tp in tps], [False] * len(tps), align)
-        layouts.append((offs, packed, total))
-    slot_bytes = max(total for _, _, total in layouts)
-    slot_bytes = (slot_bytes + 511) // 512 * 512
+    # everything below that depends only on the clique's tensor structure is computed once per structure: the placeholder
+    # lists come from GroupWrapper._gather_placeholders, which hands out the same object while no member's structure changes
+    geo = _geometry(group, all_placeholders, align, world)
+    layouts, slot_bytes = geo["layouts"], geo["slot_bytes"]
 
     plan = engine._plan_for(my_tensors, [False] * len(my_tensors))
     assert list(plan.offsets) == layouts[me][0] and plan.staging_bytes == layouts[me][2]
@@ -185,18 +219,7 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
             dist.all_gather_into_tensor(whole, mine, group=group.group)
         engine.last_exchange = "nccl-allgather"
 
-    dev_lists = []
-    for r, (tps, (offs, packed, _)) in enumerate(zip(all_placeholders, layouts)):
-        lay = PackedLayout(
-            shapes=[tuple(tp.hollow_tensor.shape) for tp in tps],
-            dtypes=[dtype_name(tp.hollow_tensor.dtype) for tp in tps],
-            src_dtypes=[dtype_name(tp.hollow_tensor.dtype) for tp in tps],
-            offsets=[r * slot_bytes + o for o in offs],
-            packed_nbytes=list(packed),
-            total_bytes=world * slot_bytes,
-            align=align,
-        )
-        dev_lists.append(lay)
+    dev_lists = geo["dev_lists"]
 
     if target_device is None or torch.device(target_device).type == "cuda":
         # stay on the device: hand out copies so the exchange buffer can be reused
@@ -220,16 +243,12 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
     slot.drained_total = base + total
     engine._exchange_free = slot.done_event
 
-    result = [host_views(lay, slot.buf) for lay in dev_lists]
-    union = PackedLayout(
-        shapes=[s for lay in dev_lists for s in lay.shapes],
-        dtypes=[d for lay in dev_lists for d in lay.dtypes],
-        src_dtypes=[d for lay in dev_lists for d in lay.src_dtypes],
-        offsets=[o for lay in dev_lists for o in lay.offsets],
-        packed_nbytes=[n for lay in dev_lists for n in lay.packed_nbytes],
-        total_bytes=total,
-        align=align,
-    )
+    # host views of a (slot buffer, structure) pair are built once: 4 us per tensor is 50 ms for 8 x 1455 tensors otherwise
+    views = slot.__dict__.get("_exchange_views")
+    if views is None or views[0] != slot.buf.name or views[1] is not dev_lists:
+        views = slot.__dict__["_exchange_views"] = (slot.buf.name, dev_lists, [host_views(lay, slot.buf) for lay in dev_lists])
+    result = [list(v) for v in views[2]]
+    union = geo["union"]
     snap = Snapshot(engine=engine, slot=slot, layout=union, progress_target=slot.drained_total, n_total=len(union.shapes))
     return result, [snap]
 

@@ -20,6 +20,7 @@ class TensorPlaceholder:
     def __init__(self, tensor: torch.Tensor):
         self.hollow_tensor = torch.empty_like(tensor, device="meta")
         self.orig_device_type = tensor.device.type
+        self._nbytes = tensor.numel() * tensor.element_size()  # asked for several times per exchange and placeholder
 
     @property
     def device(self):
@@ -27,7 +28,8 @@ class TensorPlaceholder:
 
     @property
     def nbytes(self) -> int:
-        return self.hollow_tensor.numel() * self.hollow_tensor.element_size()
+        cached = self.__dict__.get("_nbytes")  # absent on placeholders unpickled from an older peer
+        return cached if cached is not None else self.hollow_tensor.numel() * self.hollow_tensor.element_size()
 
     def empty_like(self, device=None):
         """Uninitialised tensor of the recorded shape on ``device`` (default: local device of the original type)."""

@@ -178,3 +178,36 @@ def test_explicit_staging_offsets_follow_a_checkpoint_container(built_library):
         plan_for(ptrs, nbytes, staging_offsets=[o + 8 for o in offs])      # not 16-byte aligned
     with pytest.raises(SnapError):
         plan_for(ptrs, nbytes, staging_offsets=[0, 64, 128, 256, 512])     # overlapping
+
+
+def test_exchange_geometry_is_computed_once_per_structure(built_library):
+    """b200/exchange._geometry: per-member layouts inside the exchange buffer (the oracle's layout rule, shifted by the member's
+    slice) and their union; the result is reused while the gathered placeholder lists are the same object."""
+    import torch
+
+    from nvidia_resiliency_ext.checkpointing.b200.exchange import _geometry
+    from nvidia_resiliency_ext.checkpointing.local.replication.torch_device_utils import TensorPlaceholder
+
+    class Group:  # stands in for GroupWrapper: only its attribute dict is used
+        pass
+
+    members = [
+        [torch.empty(5, 7), torch.empty(3, dtype=torch.int64), torch.empty(0), torch.empty((), dtype=torch.bfloat16)],
+        [torch.empty(1000, 3), torch.empty(2, dtype=torch.uint8), torch.empty(4, 4), torch.empty(1)],
+    ]
+    placeholders = [[TensorPlaceholder(t) for t in tensors] for tensors in members]
+    assert [tp.nbytes for tp in placeholders[1]] == [12000, 2, 64, 4]
+    group = Group()
+    geo = _geometry(group, placeholders, 512, 2)
+    slot_bytes = geo["slot_bytes"]
+    assert slot_bytes % 512 == 0
+    for r, tensors in enumerate(members):
+        offs, packed, total = orc.pack_layout([t.numel() * t.element_size() for t in tensors], [False] * len(tensors), 512)
+        assert geo["layouts"][r] == (offs, packed, total) and total <= slot_bytes
+        lay = geo["dev_lists"][r]
+        assert lay.offsets == [r * slot_bytes + o for o in offs] and lay.packed_nbytes == packed
+        assert lay.shapes == [tuple(t.shape) for t in tensors] and lay.total_bytes == 2 * slot_bytes
+    union = geo["union"]
+    assert union.offsets == geo["dev_lists"][0].offsets + geo["dev_lists"][1].offsets and len(union.shapes) == 8
+    assert _geometry(group, placeholders, 512, 2) is geo            # same structure object: cached
+    assert _geometry(group, [list(p) for p in placeholders], 512, 2) is not geo  # a new gather result: recomputed

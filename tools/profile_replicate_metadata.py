@@ -27,13 +27,47 @@ def c2_like_state(rank, numel=4):
     return {"model": model, "optimizer": {"state": opt}, "iteration": 0}
 
 
-def job(rank, world, iters):
+def job(rank, world, iters, manager=False):
     import torch.distributed as dist
 
     from _cpu_tasd import CpuTensorAwareStateDict
     from nvidia_resiliency_ext.checkpointing.local.replication.strategies import CliqueReplicationStrategy
 
     strat = CliqueReplicationStrategy(dist.group.WORLD, target_device="cpu")
+    if manager:
+        import tempfile
+
+        from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+        mgr = LocalCheckpointManager(tempfile.mkdtemp(prefix="nvrx_prof_", dir="/dev/shm"), repl_strategy=strat)
+        for it in range(iters):
+            sd = c2_like_state(rank)
+            sd["iteration"] = it
+            tasd = CpuTensorAwareStateDict(sd)
+            dist.barrier()
+            prof = None
+            if rank == 0 and it == iters - 1 and os.environ.get("PROFILE"):
+                import cProfile
+
+                prof = cProfile.Profile()
+                prof.enable()
+            t0 = time.perf_counter()
+            req = mgr.save(tasd, it + 1, is_async=True)
+            dt = time.perf_counter() - t0
+            if prof is not None:
+                import pstats
+
+                prof.disable()
+                pstats.Stats(prof).sort_stats("cumulative").print_stats(30)
+            t1 = time.perf_counter()
+            req.execute_sync()
+            if rank == 0:
+                print(f"iter {it}: manager.save() returned after {dt * 1e3:.1f} ms; write+finalize {1e3 * (time.perf_counter() - t1):.0f} ms", flush=True)
+        import shutil
+
+        dist.barrier()
+        shutil.rmtree(mgr.local_ckpt_dir, ignore_errors=True)
+        return
     for it in range(iters):
         sd = c2_like_state(rank)
         sd["iteration"] = it  # a changing non-tensor leaf, as a trainer would have
@@ -62,7 +96,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ranks", type=int, default=8)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--manager", action="store_true", help="time LocalCheckpointManager.save(is_async=True) instead of replicate()")
     a = ap.parse_args()
     from _mp import run_ranks
 
-    run_ranks(job, a.ranks, a.iters)
+    run_ranks(job, a.ranks, a.iters, a.manager, timeout=600)
