@@ -821,6 +821,7 @@ class SnapshotEngine:
         out: Optional[Sequence[torch.Tensor]] = None,
         resident: Optional[Tuple[_Slot, Sequence[int]]] = None,
         file_source: Optional[Tuple[str, Sequence[int]]] = None,
+        expect_crcs: Optional[Sequence[int]] = None,
     ) -> List[torch.Tensor]:
         """CPU tensors -> CUDA tensors of this device with one H2D copy and one scatter kernel.
 
@@ -829,7 +830,10 @@ class SnapshotEngine:
         offsets (the checkpoint file is a hard link to the slot), so the gather into a pinned buffer is skipped and the
         H2D reads the slot directly.
         ``file_source = (path, file offsets)`` (from ``ptzip.tensor_offsets_in_file``): fill the pinned slot with parallel
-        ``pread`` from the checkpoint file instead of a memcpy from the tensors' mmap (no page-by-page faults)."""
+        ``pread`` from the checkpoint file instead of a memcpy from the tensors' mmap (no page-by-page faults).
+        ``expect_crcs[i]``: crc32 the bytes of tensor i must have (from the file's directory; 0 = unknown).  The checksum
+        kernel sums what actually ARRIVED in HBM, so a flipped bit in the file, the page cache, the pinned slot or on the way
+        over PCIe fails the restore (``SnapError``) instead of silently resuming training from corrupt weights."""
         host_tensors = [t.detach() for t in host_tensors]
         target_dtypes = [
             (widen_to[i] if widen_to is not None and widen_to[i] is not None else t.dtype)
@@ -877,12 +881,30 @@ class SnapshotEngine:
                 self.lib.nvrx_fill(staging.ptr, slot.buf.data_ptr, plan.staging_bytes, self.drain_chunk, stream, None),
                 "nvrx_fill",
             )
+            crc = values = None
+            if expect_crcs is not None and any(expect_crcs):
+                assert len(expect_crcs) == len(out)
+                crc = CrcPlan(plan.offsets, plan.packed_nbytes, self.device)
+                values = torch.zeros(crc.n_values + 2, dtype=torch.int32).pin_memory()
+                crc.run(staging.ptr, values.data_ptr(), 0, 0, stream)  # same stream: after the H2D, before anything reuses staging
+                self.launches += 1
             plan.scatter(staging.ptr, stream)
             self.launches += 1 if plan.n_tiles else 0
             done = Event(self.device)
             done.record(stream)
             self._staging_free = done
             done.synchronize()  # the pinned slot is reused; restore is a blocking call like the reference's
+            if crc is not None:
+                # the < 512 left-over bytes per tensor are summed from the pinned slot the H2D read from
+                got = finish_crcs(plan.offsets, plan.packed_nbytes, values.data_ptr(), crc.n_values, slot.buf.data_ptr)
+                crc.close()
+                bad = [i for i, (g, e, nb) in enumerate(zip(got, expect_crcs, plan.packed_nbytes)) if nb and e and g != e]
+                if bad:
+                    raise SnapError(
+                        _cabi.E_STATE, "verifying restored tensors",
+                        f"crc32 mismatch on {len(bad)} of {len(out)} tensors (first: #{bad[0]}, got {got[bad[0]]:#010x}, "
+                        f"file says {expect_crcs[bad[0]]:#010x}) -- the checkpoint is corrupt",
+                    )
         finally:
             self._release(slot)
         return out

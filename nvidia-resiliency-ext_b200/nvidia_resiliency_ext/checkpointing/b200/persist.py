@@ -9,6 +9,7 @@ imports the CUDA side of the engine and never calls CUDA.  The functions are mod
 from __future__ import annotations
 
 import os
+from contextlib import contextmanager
 from typing import Any, Dict, List
 
 import torch
@@ -16,17 +17,26 @@ import torch
 DRAIN_TIMEOUT_MS = int(os.environ.get("NVRX_B200_DRAIN_TIMEOUT_MS", str(30 * 60 * 1000)))
 
 
-def fast_zip_writes() -> None:
-    """Writer-process setting: do not compute zip CRC32s in ``torch.save``.
+@contextmanager
+def fast_zip_writes():
+    """While saving a snapshot: do not compute zip CRC32s in ``torch.save``.
 
     ``torch.load`` never verifies them (checked with a zeroed CRC field, plain and ``mmap=True`` loads), but
     computing them is the dominant cost of ``torch.save`` for multi-GB payloads (single-threaded crc32 over the
-    whole snapshot).  ``NVRX_B200_ZIP_CRC=1`` keeps them."""
+    whole snapshot).  ``NVRX_B200_ZIP_CRC=1`` keeps them.  The process-wide PyTorch switch is put back afterwards: a
+    synchronous save runs in the trainer, whose own ``torch.save`` calls must keep their checksums."""
+    previous = None
     if os.environ.get("NVRX_B200_ZIP_CRC", "0") in ("", "0"):
         try:
+            previous = torch.serialization.get_crc32_options()
             torch.serialization.set_crc32_options(False)
         except Exception:  # noqa: BLE001 - older PyTorch without the switch
-            pass
+            previous = None
+    try:
+        yield
+    finally:
+        if previous is not None:
+            torch.serialization.set_crc32_options(previous)
 
 
 def drain_aware(fn):
@@ -123,8 +133,7 @@ def save_snapshot_with_torch(skeleton: Any, path, desc: Dict, *save_args, **save
     views = host_views(desc["layout"], hb)
     try:
         obj = _materialise(skeleton, views)
-        fast_zip_writes()
-        with fastsave.slot_ranges(fastsave.ranges_for([desc], [hb])):
+        with fast_zip_writes(), fastsave.slot_ranges(fastsave.ranges_for([desc], [hb])):
             fastsave.save(obj, path, *save_args, **save_kwargs)
     finally:
         del views

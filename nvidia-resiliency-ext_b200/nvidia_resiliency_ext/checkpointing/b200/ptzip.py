@@ -397,3 +397,23 @@ def tensor_offsets_in_file(path, tensors: Sequence[torch.Tensor]) -> Optional[Li
         offs.append(off)
         end = off + nb
     return offs
+
+
+def record_crcs(path, n_storages: int) -> Optional[List[int]]:
+    """CRC-32 fields of the records ``data/0 .. data/n-1`` of a checkpoint file (from its central directory), or None when the
+    file is not such an archive.  A zero field on a non-empty record means "written without checksums" (our fast writers'
+    default; PyTorch's own writer and the GPU-checksum mode fill them in)."""
+    import zipfile
+
+    try:
+        with zipfile.ZipFile(path) as zf:
+            by_key = {}
+            for info in zf.infolist():
+                head, sep, key = info.filename.rpartition("/data/")
+                if sep and key.isdigit() and "/" not in head:
+                    by_key[int(key)] = info.CRC
+    except (OSError, zipfile.BadZipFile):
+        return None
+    if sorted(by_key) != list(range(n_storages)):
+        return None
+    return [by_key[i] for i in range(n_storages)]

@@ -146,9 +146,13 @@ class BasicTensorAwareStateDict(TensorAwareStateDict):
         # set by LocalCheckpointManager._load in zero-copy mode: the file may be a hard link to a slot that is still pinned in
         # this process (in-process restart), in which case the H2D reads the slot and nothing is copied on the host
         source = self.__dict__.pop("_b200_loaded_from", None)
-        resident = file_source = None
+        resident = file_source = expect = None
         if source is not None and len(host) == len(current):
             from ..b200 import fastsave, ptzip
+
+            if os.environ.get("NVRX_B200_VERIFY_RESTORE", "0") == "1":
+                # opt-in: check what arrives in HBM against the record checksums of the file (GPU kernel, see engine.restore)
+                expect = ptzip.record_crcs(source, len(host))
 
             if fastsave.zero_copy_enabled():
                 resident = engine.resident_source(source, host)
@@ -156,5 +160,5 @@ class BasicTensorAwareStateDict(TensorAwareStateDict):
                 # opt-in (to be measured): fill the pinned slot by parallel pread from the file instead of from its mmap
                 offs = ptzip.tensor_offsets_in_file(source, host)
                 file_source = (source, offs) if offs is not None else None
-        moved = iter(engine.restore(host, widen_to=widen_to, resident=resident, file_source=file_source))
+        moved = iter(engine.restore(host, widen_to=widen_to, resident=resident, file_source=file_source, expect_crcs=expect))
         self._replace_tensors([t if t.is_cuda else next(moved) for t in current])

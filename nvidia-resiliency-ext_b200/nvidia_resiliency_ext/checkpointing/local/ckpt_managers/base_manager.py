@@ -17,6 +17,7 @@ Set ``NVRX_B200_EAGER_SYNC=1`` to wait for the drain before ``save`` returns (re
 import logging
 import os
 from abc import ABC, abstractmethod
+from contextlib import nullcontext
 from collections import defaultdict
 from concurrent.futures import ThreadPoolExecutor
 from typing import Any, Iterable, Optional, Tuple
@@ -110,12 +111,10 @@ class BaseCheckpointManager(ABC):
     @_disable_gc()
     def _save_fn(self, id_to_state_dict, snapshot_descs=()):
         held = wait_for_snapshots(snapshot_descs)  # CPU-only wait for the drain(s); no CUDA in the writer
-        if snapshot_descs:
-            fast_zip_writes()
         ckpt_id = None
         try:
             # backends that save through b200.fastsave.save() get the payload written in parallel from the slots
-            with fastsave.slot_ranges(fastsave.ranges_for(snapshot_descs, held)):
+            with (fast_zip_writes() if snapshot_descs else nullcontext()), fastsave.slot_ranges(fastsave.ranges_for(snapshot_descs, held)):
                 for ckpt_id, state_dict in id_to_state_dict.items():
                     try:
                         self._save(state_dict, ckpt_id)

@@ -22,6 +22,7 @@ barriers around it); otherwise pack + ONE ``dist.all_to_all_single`` (NCCL, or g
 from __future__ import annotations
 
 import logging
+from contextlib import nullcontext
 import os
 import pickle
 import re
@@ -196,9 +197,7 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
         """Writer side (forked child or inline): own full file, then one file per received fragment."""
         held = wait_for_snapshots(snapshot_descs)
         try:
-            if snapshot_descs:
-                fast_zip_writes()
-            with fastsave.slot_ranges(fastsave.ranges_for(snapshot_descs, held)):
+            with (fast_zip_writes() if snapshot_descs else nullcontext()), fastsave.slot_ranges(fastsave.ranges_for(snapshot_descs, held)):
                 for ckpt_id, sd in id_to_state_dict.items():
                     self._save(sd, ckpt_id)
                 for spec in frag_specs:

@@ -79,3 +79,33 @@ def test_published_checkpoint_has_valid_record_checksums(shm_dir, dist_1rank, bu
             sd["p0"].add_(1.0)
     finally:
         ckpt.close()
+
+
+def test_restore_verification_catches_a_flipped_bit(tmp_path, dist_1rank, built_library, monkeypatch):
+    """NVRX_B200_VERIFY_RESTORE=1: the checksum kernel sums what arrived in HBM and compares with the file's directory."""
+    from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
+    from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+    monkeypatch.setenv("NVRX_B200_VERIFY_RESTORE", "1")
+    monkeypatch.setenv("NVRX_B200_ZIP_CRC", "1")  # the copying writer fills the CRC fields in (CPU threads)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    sd = {f"p{i}": torch.randn(513 + i, 255, device="cuda", generator=g) for i in range(8)}
+    mgr = LocalCheckpointManager(tmp_path)
+    mgr.save(BasicTensorAwareStateDict({k: v.clone() for k, v in sd.items()}), 3, is_async=False)
+    assert mgr.find_latest() == 3
+    loaded, _ = mgr.load()  # intact file: passes
+    assert all(torch.equal(loaded.state_dict[k], v) for k, v in sd.items())
+    path = mgr._local_ckpt_path_from_id(mgr._ckpt_id(3))
+    reader = torch._C.PyTorchFileReader(str(path))
+    off = reader.get_record_offset("data/5") + 70_001
+    del reader
+    with open(path, "r+b") as fh:
+        fh.seek(off)
+        byte = fh.read(1)
+        fh.seek(off)
+        fh.write(bytes([byte[0] ^ 0x10]))
+    mgr2 = LocalCheckpointManager(tmp_path)
+    assert mgr2.find_latest() == 3
+    with pytest.raises(SnapError, match="crc32 mismatch"):
+        mgr2.load()

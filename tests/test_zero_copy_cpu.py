@@ -267,3 +267,17 @@ def _check_archive(target, state):
             tensors = orc.flatten_tensors(state)
             for i, t_ in enumerate(tensors):
                 assert zf.getinfo(f"{archive}/data/{i}").CRC == zlib.crc32(t_.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if t_.numel() else b"")
+
+
+def test_record_crcs_reads_the_directory(built_library, tmp_path):
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+
+    state = _state()
+    tensors = orc.flatten_tensors(state)
+    path = tmp_path / "plain.pt"
+    torch.save(state, path)  # PyTorch's own writer fills the CRC fields in
+    want = [zlib.crc32(t.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if t.numel() else b"") for t in tensors]
+    assert ptzip.record_crcs(path, len(tensors)) == want
+    assert ptzip.record_crcs(path, len(tensors) + 1) is None  # not one record per tensor
+    (tmp_path / "junk.pt").write_bytes(b"not a zip")
+    assert ptzip.record_crcs(tmp_path / "junk.pt", 1) is None and ptzip.record_crcs(tmp_path / "missing.pt", 1) is None
