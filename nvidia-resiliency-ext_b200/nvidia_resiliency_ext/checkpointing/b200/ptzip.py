@@ -354,7 +354,10 @@ def publish_slot(
         write_container(fd, lay, small, file_size=file_size, crcs=crcs, pad_crc=False)
     finally:
         os.close(fd)
-    tmp = f"{target}.nvrx{os.getpid()}"
+    # temporary link name: keeps the target's extension so that a manager's cleanup glob (iter_*_local*.pt) also removes a
+    # leftover from a writer that died between the two calls below (it would pin the slot forever otherwise)
+    root, ext = os.path.splitext(os.fspath(target))
+    tmp = f"{root}.nvrx{os.getpid()}{ext}"
     try:
         if os.path.lexists(tmp):
             os.unlink(tmp)
