@@ -21,7 +21,9 @@ There is no CPU fallback: everything here raises if ``libnvrx_snap.so`` or a CUD
 from __future__ import annotations
 
 import ctypes as C
+import logging
 import os
+import re
 import threading
 import uuid
 from dataclasses import dataclass, field
@@ -31,6 +33,8 @@ import torch
 
 from . import _cabi
 from ._cabi import SnapError, check
+
+logger = logging.getLogger(__name__)
 
 DEFAULT_ALIGN = 512
 DEFAULT_DRAIN_CHUNK = int(os.environ.get("NVRX_B200_DRAIN_CHUNK_MB", "256")) << 20
@@ -548,6 +552,49 @@ def choose_slot(slots: Sequence[_Slot], nbytes: int, max_slots: int) -> Tuple[Op
     return pick, False
 
 
+_SLOT_NAME = re.compile(r"^nvrx_b200_(\d+)_(\d+)_[0-9a-f]{8}_s\d+_g\d+$")
+_reaped = False
+
+
+def _pid_namespace() -> int:
+    try:
+        return os.stat("/proc/self/ns/pid").st_ino
+    except OSError:
+        return 0
+
+
+def reap_stale_slots(shm_dir: str = "/dev/shm") -> List[str]:
+    """Remove snapshot slots whose owner died without running its exit handler (SIGKILL, OOM kill, node-local crash): each is
+    a shared-memory object as large as a snapshot and would otherwise stay until reboot, counting against the container's
+    memory.  A slot belongs to a dead owner when its name carries this PID namespace and a PID that no longer exists.  Only
+    the shm NAME is removed: a checkpoint file that is a hard link to the slot (zero-copy persistence) keeps its pages, which is
+    the point of a local checkpoint.  Returns the names removed."""
+    removed = []
+    ns = _pid_namespace()
+    try:
+        names = os.listdir(shm_dir)
+    except OSError:
+        return removed
+    for name in names:
+        m = _SLOT_NAME.match(name)
+        if not m or int(m.group(1)) != ns:
+            continue
+        pid = int(m.group(2))
+        try:
+            os.kill(pid, 0)
+            continue  # alive (or not ours to signal: PermissionError below)
+        except ProcessLookupError:
+            pass
+        except OSError:
+            continue
+        try:
+            os.unlink(os.path.join(shm_dir, name))
+            removed.append(name)
+        except OSError:
+            pass
+    return removed
+
+
 class SnapshotEngine:
     """Per-(process, device) snapshot engine.  Thread-compatible: call from the training thread."""
 
@@ -579,7 +626,13 @@ class SnapshotEngine:
         self.drain_chunk = drain_chunk
         self.timing = timing
         self.prefault_threads = prefault_threads if prefault_threads is not None else min(16, os.cpu_count() or 1)
-        self.shm_prefix = shm_prefix or f"/nvrx_b200_{os.getpid()}_{uuid.uuid4().hex[:8]}"
+        self.shm_prefix = shm_prefix or f"/nvrx_b200_{_pid_namespace()}_{os.getpid()}_{uuid.uuid4().hex[:8]}"
+        global _reaped
+        if not _reaped and os.environ.get("NVRX_B200_NO_REAP", "0") != "1":
+            _reaped = True
+            stale = reap_stale_slots()
+            if stale:
+                logger.warning(f"removed {len(stale)} snapshot slot(s) left behind by dead processes: {stale[:4]}...")
         self._plans: Dict[tuple, Plan] = {}
         self._staging: Optional[DeviceBuffer] = None
         self._staging_free: Optional[Event] = None  # recorded when the last reader of staging finished

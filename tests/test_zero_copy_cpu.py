@@ -281,3 +281,31 @@ def test_record_crcs_reads_the_directory(built_library, tmp_path):
     assert ptzip.record_crcs(path, len(tensors) + 1) is None  # not one record per tensor
     (tmp_path / "junk.pt").write_bytes(b"not a zip")
     assert ptzip.record_crcs(tmp_path / "junk.pt", 1) is None and ptzip.record_crcs(tmp_path / "missing.pt", 1) is None
+
+
+def test_slots_of_dead_owners_are_reaped(tmp_path):
+    """A killed trainer cannot unlink its slots; the next engine start removes them -- but only names of THIS pid namespace
+    whose pid is gone, and never a checkpoint that was published from such a slot."""
+    import subprocess
+    import sys
+
+    from nvidia_resiliency_ext.checkpointing.b200.engine import _pid_namespace, reap_stale_slots
+
+    dead = subprocess.Popen([sys.executable, "-c", "pass"])
+    dead.wait()
+    ns = _pid_namespace()
+    names = {
+        "dead": f"nvrx_b200_{ns}_{dead.pid}_0123abcd_s0_g1",
+        "dead_published": f"nvrx_b200_{ns}_{dead.pid}_0123abcd_s1_g2",
+        "alive": f"nvrx_b200_{ns}_{os.getpid()}_0123abcd_s0_g1",
+        "other_namespace": f"nvrx_b200_{ns + 1}_{dead.pid}_0123abcd_s0_g1",
+        "not_a_slot": f"nvrx_b200_test_{dead.pid}_whatever",
+    }
+    for n in names.values():
+        (tmp_path / n).write_bytes(b"x" * 10)
+    os.link(tmp_path / names["dead_published"], tmp_path / "iter_0000001_0_local.pt")
+    removed = reap_stale_slots(str(tmp_path))
+    assert sorted(removed) == sorted([names["dead"], names["dead_published"]])
+    left = set(os.listdir(tmp_path))
+    assert left == {names["alive"], names["other_namespace"], names["not_a_slot"], "iter_0000001_0_local.pt"}
+    assert (tmp_path / "iter_0000001_0_local.pt").read_bytes() == b"x" * 10 and os.stat(tmp_path / "iter_0000001_0_local.pt").st_nlink == 1
