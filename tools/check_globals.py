@@ -35,6 +35,27 @@ def check_module(mod) -> list:
     return problems
 
 
+def check_abi_calls() -> list:
+    """Every ``<something>.nvrx_xxx(...)`` call in the package must name an exported symbol and pass as many arguments as the
+    ctypes signature declares (ctypes only checks that at call time -- on a GPU box)."""
+    import ast
+
+    from nvidia_resiliency_ext.checkpointing.b200 import _cabi
+
+    lib = _cabi.lib()
+    problems = []
+    for path in list((ROOT / "nvidia-resiliency-ext_b200" / "nvidia_resiliency_ext").rglob("*.py")) + [ROOT / "bench.py", ROOT / "__graft_entry__.py"] + list((ROOT / "tools").glob("*.py")):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and node.attr.startswith("nvrx_") and node.attr not in _cabi.EXPORTED_SYMBOLS and node.attr != "nvrx_drain_aware":
+                problems.append(f"{path}:{node.lineno}: {node.attr} is not an exported symbol")
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in _cabi.EXPORTED_SYMBOLS:
+                want = len(getattr(lib, node.func.attr).argtypes or [])
+                if not any(isinstance(a, ast.Starred) for a in node.args) and len(node.args) != want:
+                    problems.append(f"{path}:{node.lineno}: {node.func.attr} called with {len(node.args)} arguments, signature has {want}")
+    return problems
+
+
 def main():
     import nvidia_resiliency_ext
 
@@ -47,7 +68,8 @@ def main():
             print(f"skip {name}: {type(exc).__name__}: {exc}")
             continue
         problems += check_module(mod)
-    print("\n".join(problems) if problems else f"{len(mods) + 2} modules: no undefined globals")
+    problems += check_abi_calls()
+    print("\n".join(problems) if problems else f"{len(mods) + 2} modules: no undefined globals, C-ABI calls match their signatures")
     return 1 if problems else 0
 
 
