@@ -261,6 +261,15 @@ class FileSystemWriterAsync(FileSystemWriter):
                 self._snapshot = None
             self._payload = None
 
+    def __del__(self):
+        # a save that was aborted (in-process restart) never reaches retrieve_write_results: give its host slot back
+        snap, self._snapshot = getattr(self, "_snapshot", None), None
+        if snap is not None:
+            try:
+                snap.release()
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+
     def prepare_decentralized_global_plan(self, local_plan: SavePlan) -> SavePlan:
         """Storage prefix for planning without a reduce_scatter: files of rank r start with ``__r_``."""
         import dataclasses

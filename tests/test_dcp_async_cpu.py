@@ -332,3 +332,43 @@ def test_matches_the_references_own_async_checkpoint(tmp_path, dist_1rank):
         assert names == sorted(f for f in os.listdir(tmp_path / "ours") if f.endswith(".distcp"))
         _, mismatch, errors = filecmp.cmpfiles(GOLDEN / "dcp_reference", tmp_path / "ours", names, shallow=False)
         assert not mismatch and not errors, (mismatch, errors)
+
+
+def test_abort_with_a_pending_dcp_save_and_resume(tmp_path, dist_1rank):
+    """In-process restart: abort_nvrx_checkpoint() stops the writer workers of every queue, also with a DCP save in flight; the
+    queues work again afterwards and a queue dropped right after an abort shuts down cleanly (reference
+    test_async_writer.py::test_async_cp_with_multiple_queue_and_abort[_followed_by_delete])."""
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue, AsyncRequest, abort_nvrx_checkpoint
+
+    state = _state()
+    q_dcp, q_plain = AsyncCallsQueue(persistent=True), AsyncCallsQueue(persistent=True)
+    try:
+        _async_save(state, tmp_path / "a", q_dcp)
+        q_plain.schedule_async_request(AsyncRequest(torch.save, ({"x": torch.arange(4)}, tmp_path / "plain_a.pt"), []))
+        q_dcp.maybe_finalize_async_calls(blocking=True)
+        q_plain.maybe_finalize_async_calls(blocking=True, no_dist=True)
+        _loaded_equals(tmp_path / "a", _state())
+
+        abort_nvrx_checkpoint()
+        for q in (q_dcp, q_plain):
+            caller = q._get_async_caller()
+            assert caller is None or caller._debug_is_async_process_running() is False
+            assert q.get_num_unfinalized_calls() == 0
+
+        # seamless resume: same queues, new workers
+        _async_save(state, tmp_path / "b", q_dcp)
+        q_plain.schedule_async_request(AsyncRequest(torch.save, ({"x": torch.arange(4)}, tmp_path / "plain_b.pt"), []))
+        q_dcp.maybe_finalize_async_calls(blocking=True)
+        q_plain.maybe_finalize_async_calls(blocking=True, no_dist=True)
+        _loaded_equals(tmp_path / "b", _state())
+        assert torch.equal(torch.load(tmp_path / "plain_b.pt")["x"], torch.arange(4))
+        for q in (q_dcp, q_plain):
+            assert q._get_async_caller()._debug_is_async_process_running() is True
+
+        # an exception in the trainer right after scheduling, abort, then the queue object goes away
+        _async_save(state, tmp_path / "c", q_dcp)
+        abort_nvrx_checkpoint()
+        q_dcp.__del__()
+    finally:
+        q_dcp.close()
+        q_plain.close()
