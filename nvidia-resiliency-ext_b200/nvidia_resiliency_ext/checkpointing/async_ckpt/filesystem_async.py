@@ -185,7 +185,8 @@ class FileSystemWriterAsync(FileSystemWriter):
     @staticmethod
     def write_preloaded_data(ctor, thread_count: int, separation_hint, rank: int, payload: dict, results_queue) -> None:
         """Write the files of this rank with PyTorch's ``FileSystemWriter`` from staged host data; the outcome (list of
-        ``WriteResult`` or a wrapped exception) is reported on ``results_queue``.  Never raises."""
+        ``WriteResult`` or a wrapped exception) is reported on ``results_queue``.  Errors are reported, not raised; only a
+        ``SystemExit`` / ``KeyboardInterrupt`` (the worker is being aborted) passes through, without a report."""
         outcome = None
         held = []
         try:
@@ -216,13 +217,13 @@ class FileSystemWriterAsync(FileSystemWriter):
                 outcome = writer.write_data(payload["plan"], _HostPlanner(staged)).wait()
             if outcome is None:
                 outcome = []
-        except BaseException as exc:  # noqa: BLE001 - reported to the trainer, raised there on the coordinator
+        except Exception as exc:  # noqa: BLE001 - reported to the trainer, raised there on the coordinator
             logger.error(f"rank {rank}: checkpoint write failed: {exc}", exc_info=True)
             outcome = _wrap_exception(exc)
         finally:
             for hb in held:
                 hb.close(unlink=False)
-            results_queue.put((rank, outcome))
+        results_queue.put((rank, outcome))
 
     # ---- stage 3 (trainer) ------------------------------------------------------------------------
     def write_data(self, plan: SavePlan, planner: SavePlanner):
