@@ -595,6 +595,10 @@ def reap_stale_slots(shm_dir: str = "/dev/shm") -> List[str]:
     return removed
 
 
+def spare_slots(slots: Sequence[_Slot], max_slots: int) -> int:
+    return sum(1 for s in slots if not s.busy and not s.published()) + max(0, max_slots - len(slots))
+
+
 class SnapshotEngine:
     """Per-(process, device) snapshot engine.  Thread-compatible: call from the training thread."""
 
@@ -715,6 +719,10 @@ class SnapshotEngine:
     def _release(self, slot: _Slot) -> None:
         slot.busy = False
 
+    def _spare_slots(self) -> int:
+        """Slots a snapshot could go to without giving up a published checkpoint: idle unpublished ones plus pool headroom."""
+        return spare_slots(self._slots, self.max_host_slots)
+
     def reserve(self, nbytes: int) -> None:
         """Pre-allocate staging and every host slot for snapshots of up to ``nbytes`` packed bytes (pinning
         16 GB takes seconds; do it once at start-up instead of inside the first save)."""
@@ -778,6 +786,10 @@ class SnapshotEngine:
 
             container = zero_copy_enabled()
         container = bool(container) and not passthrough and len(cuda_tensors) > 0
+        if container and self._spare_slots() <= 1:
+            # every published checkpoint pins one slot until its file is deleted.  Keep the last slot that is not somebody's
+            # checkpoint for copying saves, instead of publishing it too and paying a 16 GB re-pin on the next save
+            container = False
         plan = self._plan_for(cuda_tensors, mask, container)
 
         stream = self._current_stream()

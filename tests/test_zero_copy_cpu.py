@@ -202,6 +202,17 @@ def test_slot_choice_skips_published_checkpoints(built_library, shm_dir):
         assert choose_slot(slots, 100, 3) == (slots[0], False)  # deleting the checkpoint frees its slot
         slots[0].busy = slots[2].busy = True
         assert choose_slot(slots, 100, 3) == (None, False)  # everything in flight: the engine raises
+        # headroom rule of snapshot(): publish only while another unpublished slot (or room to grow) remains
+        from nvidia_resiliency_ext.checkpointing.b200.engine import spare_slots
+
+        for s in slots:
+            s.busy = False
+        assert spare_slots(slots, 4) == 2 + 1  # slot 2 is published (link above), 0 and 1 are free, one more may be created
+        link(0)
+        assert spare_slots(slots, 4) == 1 + 1 and spare_slots(slots, 3) == 1  # at 1 the engine stops publishing
+        os.unlink(shm_dir / "iter0.pt")
+        os.unlink(shm_dir / "iter2.pt")
+        assert spare_slots(slots, 3) == 3
     finally:
         for s in slots:
             s.buf.close()
