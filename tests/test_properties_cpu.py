@@ -1,0 +1,104 @@
+"""Randomised (hypothesis) checks of the host-side building blocks against their definitions: checksum chaining vs zlib,
+container geometry invariants, and the planner's coverage in container geometry."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import torch
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from oracle import crc_oracle as co
+from oracle import snapshot_oracle as orc
+
+SETTINGS = dict(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+
+sizes_strategy = st.lists(
+    st.one_of(st.integers(0, 2048), st.integers(60_000, 70_000), st.integers(0, 300_000)), min_size=1, max_size=12
+)
+
+
+@settings(**SETTINGS)
+@given(sizes=sizes_strategy, shifts=st.lists(st.sampled_from([0, 0, 0, 16, 8, 4]), min_size=12, max_size=12), seed=st.integers(0, 2**31))
+def test_crc_finish_equals_zlib(built_library, sizes, shifts, seed):
+    from nvidia_resiliency_ext.checkpointing.b200 import _cabi
+
+    offsets, cur = [], 0
+    for nb, sh in zip(sizes, shifts):
+        cur = -(-cur // 64) * 64 + sh
+        offsets.append(cur)
+        cur += nb
+    payload = np.random.default_rng(seed).integers(0, 256, cur + 16, dtype=np.uint8)
+    chunks = co.chunks_of(offsets, sizes)
+    values = [co.chunk_value(payload[o : o + r * 512].tobytes()) for o, r, _ in chunks]
+    n = len(sizes)
+    out = (C.c_uint32 * n)()
+    rc = _cabi.lib().nvrx_crc_finish(
+        n, (C.c_uint64 * n)(*offsets), (C.c_uint64 * n)(*sizes), (C.c_uint32 * max(1, len(values)))(*values), len(values),
+        payload.ctypes.data, out,
+    )
+    assert rc == 0
+    assert list(out) == [zlib.crc32(payload[o : o + nb].tobytes()) for o, nb in zip(offsets, sizes)]
+
+
+@settings(**SETTINGS)
+@given(sizes=sizes_strategy)
+def test_container_geometry_invariants(built_library, sizes):
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+    from nvidia_resiliency_ext.checkpointing.b200.engine import Plan
+
+    offsets, span = ptzip.slot_offsets(sizes)
+    lay = ptzip.slot_layout(sizes)
+    end = 0
+    for i, (off, nb, rec) in enumerate(zip(offsets, sizes, lay.records)):
+        assert off % 512 == 0 and off >= end
+        # the gap in front of the data holds that record's local header: 30 bytes + name (+ zip64 sizes), padding >= 4 or 0
+        header = rec.data_off - rec.header_off
+        assert header >= 30 + len(rec.name) and rec.header_off == ptzip.SLOT_PREFIX + end
+        end = off + nb
+    assert span == end
+    # the CUDA-free planner accepts the geometry as it is and covers every byte once
+    ptrs = [0x10000000 + 0x100000 * i if nb else 0 for i, nb in enumerate(sizes)]
+    plan = Plan(ptrs, sizes, None, device=0, staging_offsets=offsets)
+    assert list(plan.offsets) == offsets and plan.staging_bytes >= span
+    n_bulk, tiles = plan.tiles()
+    covered = [0] * len(sizes)
+    for seg, nb, _ in tiles:
+        covered[seg] += nb
+    assert covered == list(sizes)
+    plan.close()
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(
+    shapes=st.lists(st.tuples(st.sampled_from(["float32", "bfloat16", "int64", "uint8", "float64", "bool"]),
+                              st.lists(st.integers(0, 40), min_size=0, max_size=3)), min_size=1, max_size=8),
+    seed=st.integers(0, 2**31),
+)
+def test_published_slot_loads_back_for_any_mix_of_tensors(built_library, shm_dir, shapes, seed):
+    import os
+
+    from test_zero_copy_cpu import _same, _slot_with_snapshot
+    from nvidia_resiliency_ext.checkpointing.b200.persist import save_snapshot_with_torch
+
+    g = torch.Generator().manual_seed(seed)
+    state = {"t": [], "meta": {"seed": seed}}
+    for name, shp in shapes:
+        dt = getattr(torch, name)
+        base = torch.randint(0, 2 if dt == torch.bool else 100, tuple(shp), generator=g)
+        state["t"].append(base.to(dt))
+    os.environ["NVRX_B200_ZERO_COPY"] = "1"
+    slot_name = f"/nvrx_prop_{os.getpid()}_{seed}"
+    hb, desc, skeleton = _slot_with_snapshot(state, slot_name)
+    target = shm_dir / f"p{seed}.pt"
+    try:
+        save_snapshot_with_torch(skeleton, str(target), desc)
+        if any(t.numel() for t in orc.flatten_tensors(state)):
+            assert os.path.samefile("/dev/shm" + slot_name, target)
+        _same(torch.load(target, weights_only=False), state)
+        _same(torch.load(target, weights_only=False, mmap=True), state)
+    finally:
+        os.environ.pop("NVRX_B200_ZERO_COPY", None)
+        hb.close()
+        if target.exists():
+            target.unlink()
