@@ -203,13 +203,9 @@ int nvrx_crc_run(nvrx_crc* c, const void* dev_base, uint32_t* host_values, uint6
     } else {
         // default: Z(512) replicated per lane in 128 KiB of shared memory, one 32-warp CTA per SM
         constexpr int kWarps = 32;
-        static std::once_flag attr_once;
-        static cudaError_t attr_rc = cudaSuccess;
-        std::call_once(attr_once, [] {
-            attr_rc = cudaFuncSetAttribute(nvrx::crc_chunks_private<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(nvrx::kCrcPrivateSmemBytes));
-        });
-        NVRX_CUDA(attr_rc);
+        // per device (function attributes live in the device's context); a few microseconds, so simply set it every time
+        NVRX_CUDA(cudaFuncSetAttribute(nvrx::crc_chunks_private<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(nvrx::kCrcPrivateSmemBytes)));
         const uint64_t want = (n + kWarps - 1) / kWarps;
         const uint32_t grid = static_cast<uint32_t>(want < static_cast<uint64_t>(c->sm_count) ? want : c->sm_count);
         nvrx::crc_chunks_private<kWarps><<<grid ? grid : 1, kWarps * 32, nvrx::kCrcPrivateSmemBytes, st>>>(
