@@ -140,15 +140,25 @@ def _clique_barrier(engine: SnapshotEngine, group) -> None:
     dist.all_reduce(tok, group=group.group)
 
 
-def _geometry(group, all_placeholders, align: int, world: int) -> dict:
+def _geometry(group, all_placeholders, align: int, world: int, container: bool = False) -> dict:
     """Per-member layouts inside the exchange buffer, as PackedLayouts and as one union layout; cached on the group for as
-    long as the gathered placeholder lists are the same object."""
+    long as the gathered placeholder lists are the same object.  ``container``: every member's slice is laid out in
+    checkpoint-container geometry (``ptzip.slot_offsets``), so that it can be drained into a slot of its own and published as
+    that member's checkpoint file without a copy."""
     cached = group.__dict__.get("_packed_geometry")
-    if cached is not None and cached["key"] is all_placeholders and cached["align"] == align and cached["world"] == world:
+    if (cached is not None and cached["key"] is all_placeholders and cached["align"] == align and cached["world"] == world
+            and cached["container"] == container):
         return cached
     layouts = []
     for tps in all_placeholders:
-        offs, packed, total = expected_layout([tp.nbytes for tp in tps], [False] * len(tps), align)
+        sizes = [tp.nbytes for tp in tps]
+        if container:
+            from .ptzip import slot_offsets
+
+            offs, span = slot_offsets(sizes)
+            offs, packed, total = list(offs), list(sizes), -(-span // align) * align
+        else:
+            offs, packed, total = expected_layout(sizes, [False] * len(tps), align)
         layouts.append((offs, packed, total))
     slot_bytes = max(total for _, _, total in layouts)
     slot_bytes = (slot_bytes + 511) // 512 * 512
@@ -170,10 +180,55 @@ def _geometry(group, all_placeholders, align: int, world: int) -> dict:
         total_bytes=world * slot_bytes,
         align=align,
     )
-    geo = {"key": all_placeholders, "align": align, "world": world, "layouts": layouts, "slot_bytes": slot_bytes,
-           "dev_lists": dev_lists, "union": union}
+    # the same layouts relative to a member's own slice (what a per-member host slot holds)
+    own_lists = [
+        PackedLayout(shapes=lay.shapes, dtypes=lay.dtypes, src_dtypes=lay.src_dtypes, offsets=list(offs), packed_nbytes=lay.packed_nbytes,
+                     total_bytes=total, align=align)
+        for lay, (offs, _, total) in zip(dev_lists, layouts)
+    ]
+    geo = {"key": all_placeholders, "align": align, "world": world, "container": container, "layouts": layouts,
+           "slot_bytes": slot_bytes, "dev_lists": dev_lists, "own_lists": own_lists, "union": union}
     group.__dict__["_packed_geometry"] = geo
     return geo
+
+
+def _container_exchange(engine: SnapshotEngine, group, world: int) -> bool:
+    """Zero-copy persistence for replicated saves (opt-in with ``NVRX_B200_ZERO_COPY=1``, which has to be set on every
+    member): possible while the pool of EVERY member can hold one slot per clique member for this save -- the geometry of a
+    member's slice is computed by all of them, so the decision is a vote (one small tensor collective, only in this mode)."""
+    from .fastsave import zero_copy_enabled
+
+    if not zero_copy_enabled():
+        return False
+    return all(group.all_gather_int(int(engine._spare_slots() >= world)))
+
+
+def _land_per_member(engine: SnapshotEngine, geo: dict, xbuf, world: int):
+    """Drain every member's slice of the exchange buffer into a pinned slot of its own (same bytes over PCIe as one big
+    drain), so that each can become that member's checkpoint file by a hard link."""
+    from .ptzip import slot_tail_room
+
+    slot_bytes = geo["slot_bytes"]
+    result, snaps, last = [], [], None
+    for r, lay in enumerate(geo["own_lists"]):
+        slot = engine._acquire_slot(slot_bytes + slot_tail_room(len(lay.shapes)))
+        base = slot.drained_total
+        check(
+            engine.lib.nvrx_drain(
+                slot.buf.data_ptr, xbuf.ptr + r * slot_bytes, lay.total_bytes, engine.drain_chunk, slot.buf.progress_ptr, base,
+                engine._side.handle, slot.done_event.handle,
+            ),
+            "nvrx_drain",
+        )
+        slot.drained_total = base + lay.total_bytes
+        views = slot.__dict__.get("_exchange_views")
+        if views is None or views[0] != slot.buf.name or views[1] is not lay:
+            views = slot.__dict__["_exchange_views"] = (slot.buf.name, lay, host_views(lay, slot.buf))
+        result.append(list(views[2]))
+        snaps.append(Snapshot(engine=engine, slot=slot, layout=lay, progress_target=slot.drained_total, n_total=len(lay.shapes)))
+        last = slot
+    engine._exchange_free = last.done_event  # the side stream runs the drains in order: the last one ends the reading
+    return result, snaps
 
 
 def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders, target_device):
@@ -188,10 +243,12 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
 
     # everything below that depends only on the clique's tensor structure is computed once per structure: the placeholder
     # lists come from GroupWrapper._gather_placeholders, which hands out the same object while no member's structure changes
-    geo = _geometry(group, all_placeholders, align, world)
+    to_host = not (target_device is None or torch.device(target_device).type == "cuda")
+    container = to_host and _container_exchange(engine, group, world)
+    geo = _geometry(group, all_placeholders, align, world, container)
     layouts, slot_bytes = geo["layouts"], geo["slot_bytes"]
 
-    plan = engine._plan_for(my_tensors, [False] * len(my_tensors))
+    plan = engine._plan_for(my_tensors, [False] * len(my_tensors), container)
     assert list(plan.offsets) == layouts[me][0] and plan.staging_bytes == layouts[me][2]
 
     xbuf, bases = shared_exchange(engine, group, world * slot_bytes)
@@ -226,12 +283,15 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
         result = [[v.clone() for v in lay.views(whole)] for lay in dev_lists]
         return result, []
 
-    # land everything in ONE pinned host slot with one drain on the side stream
-    total = world * slot_bytes
-    slot = engine._acquire_slot(total)
     packed_ev = Event(engine.device)
     packed_ev.record(stream)
     engine._side.wait_event(packed_ev)
+    if container:
+        return _land_per_member(engine, geo, xbuf, world)
+
+    # land everything in ONE pinned host slot with one drain on the side stream
+    total = world * slot_bytes
+    slot = engine._acquire_slot(total)
     base = slot.drained_total
     check(
         engine.lib.nvrx_drain(

@@ -122,6 +122,26 @@ def test_replicated_save_retrieve_restore_pairs(built_library, shm_dir):
     run_ranks(_w_replicated_save_and_restore, world, str(shm_dir), 1, 2, (1,), backend="nccl")
 
 
+def _w_replicated_zero_copy(rank, world, root, jump, factor, kill):
+    import os
+
+    os.environ["NVRX_B200_ZERO_COPY"] = "1"  # on every member: the container geometry of a slice is computed by all of them
+    _w_replicated_save_and_restore(rank, world, root, jump, factor, kill)
+    # every surviving file on this rank is a hard link to one of its pinned slots, not a copy
+    from pathlib import Path
+
+    files = [p for p in Path(root).rglob("iter_*_local.pt")]
+    mine = [p for p in files if f"/{rank}/" in str(p)]
+    assert rank in kill or (mine and all(os.stat(p).st_nlink == 2 for p in mine)), [(str(p), os.stat(p).st_nlink) for p in mine]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="opt-in mode, not yet validated on a B200")
+def test_replicated_save_zero_copy_pairs(built_library, shm_dir):
+    """Replicated zero-copy (written after round 1's GPU budget was spent): each member's slice of the exchange buffer is
+    drained into a slot of its own in container geometry and published as that member's file."""
+    run_ranks(_w_replicated_zero_copy, 2, str(shm_dir), 1, 2, (1,), backend="nccl")
+
+
 def test_replicated_save_retrieve_restore_full_clique(built_library, shm_dir):
     world = min(torch.cuda.device_count(), 8)
     if world < 4:

@@ -211,3 +211,34 @@ def test_exchange_geometry_is_computed_once_per_structure(built_library):
     assert union.offsets == geo["dev_lists"][0].offsets + geo["dev_lists"][1].offsets and len(union.shapes) == 8
     assert _geometry(group, placeholders, 512, 2) is geo            # same structure object: cached
     assert _geometry(group, [list(p) for p in placeholders], 512, 2) is not geo  # a new gather result: recomputed
+
+
+def test_exchange_geometry_in_container_mode(built_library):
+    """Replicated zero-copy: every member's slice of the exchange buffer carries the container geometry of that member's
+    tensors, so that it can be drained into its own slot and published as that member's file."""
+    import torch
+
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+    from nvidia_resiliency_ext.checkpointing.b200.exchange import _geometry
+    from nvidia_resiliency_ext.checkpointing.local.replication.torch_device_utils import TensorPlaceholder
+
+    class Group:
+        pass
+
+    members = [[torch.empty(5, 7), torch.empty(0), torch.empty(3, dtype=torch.int64)], [torch.empty(1000, 3), torch.empty(1)]]
+    placeholders = [[TensorPlaceholder(t) for t in tensors] for tensors in members]
+    group = Group()
+    dense = _geometry(group, placeholders, 512, 2)
+    geo = _geometry(group, placeholders, 512, 2, container=True)
+    assert geo is not dense and geo["container"] and _geometry(group, placeholders, 512, 2, container=True) is geo
+    for r, tensors in enumerate(members):
+        sizes = [t.numel() * t.element_size() for t in tensors]
+        offs, span = ptzip.slot_offsets(sizes)
+        assert geo["layouts"][r][0] == offs and geo["layouts"][r][2] >= span
+        assert geo["own_lists"][r].offsets == offs and geo["own_lists"][r].total_bytes == geo["layouts"][r][2]
+        assert geo["dev_lists"][r].offsets == [r * geo["slot_bytes"] + o for o in offs]
+        # the planner of member r produces exactly these offsets for its own tensors
+        plan = plan_for([0x1000000 * (i + 1) if n else 0 for i, n in enumerate(sizes)], sizes, staging_offsets=offs)
+        assert list(plan.offsets) == offs and plan.staging_bytes == geo["layouts"][r][2]
+        plan.close()
+    assert geo["slot_bytes"] >= max(l[2] for l in geo["layouts"]) and geo["slot_bytes"] % 512 == 0

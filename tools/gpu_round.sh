@@ -44,6 +44,11 @@ if [[ $WHAT == zerocopy ]]; then
   NVRX_B200_RESTORE_PREAD=1 guarded timeout 900 python bench.py > gpurun_out/bench_pread.json 2> gpurun_out/bench_pread.err; cat gpurun_out/bench_pread.json
   NVRX_B200_ZERO_COPY=1 NVRX_B200_GPU_CRC=1 guarded timeout 900 python bench.py > gpurun_out/bench_zerocopy.json 2> gpurun_out/bench_zerocopy.err; tail -3 gpurun_out/bench_zerocopy.err; cat gpurun_out/bench_zerocopy.json
 fi
+if [[ $WHAT == multizc ]]; then
+  # 2+ GPUs: the whole multi-GPU suite including the gated replicated zero-copy test
+  NVRX_B200_TEST_UNVALIDATED=1 guarded timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi_zc.log 2>&1
+  tail -30 gpurun_out/pytest_multi_zc.log
+fi
 if [[ $WHAT == multi ]]; then
   guarded timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi.log 2>&1
   tail -30 gpurun_out/pytest_multi.log
