@@ -160,15 +160,17 @@ def save(obj, f, *args, **kwargs) -> str:
         # a file object was opened (exclusively, by the managers) on its name: the link replaces that empty file
         if isinstance(target, str) and _try_link(obj, target, records, protocol):
             return "linked"
-    if is_path:
+    named = os.fspath(f) if is_path else getattr(f, "name", None)
+    if start == 0 and isinstance(named, str):
         # the GPU summed the records while the snapshot drained (opt-in): write our own payload-first container, whose headers
-        # take those checksums -- PyTorch's writer would either leave them zero or sum 16 GB on one core
+        # take those checksums -- PyTorch's writer would either leave them zero or sum 16 GB on one core.  (A file object was
+        # opened on its name by the caller, exclusively in the managers' case; the container is written through the name.)
         slot, offsets, sizes = _single_slot(records)
         info = getattr(slot, "crc_info", None) if slot is not None else None
         if info and protocol == torch.serialization.DEFAULT_PROTOCOL:
             from . import ptzip
 
-            ptzip.save(obj, f, locate=_locate_or_none, threads=WRITE_THREADS, crcs=_gpu_crcs(slot, info, offsets, sizes))
+            ptzip.save(obj, named, locate=_locate_or_none, threads=WRITE_THREADS, crcs=_gpu_crcs(slot, info, offsets, sizes))
             return "parallel+gpu-crc"
     with torch.serialization.skip_data():
         torch.save(obj, f, **kwargs)
