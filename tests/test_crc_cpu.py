@@ -101,3 +101,22 @@ def test_plan_enumerates_the_same_chunks(built_library):
     _cabi.check(lib.nvrx_crc_info(h, C.byref(n)), "nvrx_crc_info")
     assert n.value == len(co.chunks_of(offsets, sizes)) == 3 + 2
     lib.nvrx_crc_destroy(h)
+
+
+def test_reference_written_files_carry_zlib_record_checksums(built_library):
+    """Pins what "checksum parity" means: the files the REFERENCE wrote (tests/golden, made by make_golden.py) have, for every
+    tensor record, the zlib crc32 of its bytes in the ZIP directory -- the value the GPU path has to reproduce."""
+    import torch
+
+    from conftest import GOLDEN
+    from oracle import snapshot_oracle as orc
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+
+    for name in ("c1_reference_async.pt", "iter_0000007_0_local.pt"):
+        loaded = torch.load(GOLDEN / name, weights_only=False)
+        tensors = orc.flatten_tensors(loaded.state_dict if hasattr(loaded, "state_dict") else loaded)
+        crcs = ptzip.record_crcs(GOLDEN / name, len(tensors))
+        assert crcs is not None, name
+        for t, crc in zip(tensors, crcs):
+            raw = t.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if t.numel() else b""
+            assert crc == zlib.crc32(raw), name
