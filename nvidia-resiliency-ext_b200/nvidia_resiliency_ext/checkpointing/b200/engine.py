@@ -1039,7 +1039,7 @@ class SnapshotEngine:
         for ptr in [p for pm in getattr(self, "_peer_maps", {}).values() for p in pm["imported"]]:
             self.lib.nvrx_ipc_close(self.device, ptr)
         self._peer_maps = {}
-        for attr in ("_exchange_buf", "_p2p_buf"):
+        for attr in ("_exchange_buf", "_p2p_buf", "_ring_buf"):
             buf = getattr(self, attr, None)
             if buf is not None:
                 buf.close()

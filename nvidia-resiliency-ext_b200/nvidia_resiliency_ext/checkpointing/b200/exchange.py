@@ -231,6 +231,91 @@ def _land_per_member(engine: SnapshotEngine, geo: dict, xbuf, world: int):
     return result, snaps
 
 
+STREAM_CHUNK = int(os.environ.get("NVRX_B200_STREAM_CHUNK_MB", "256")) << 20
+
+
+def _allgather_streamed(engine: SnapshotEngine, group, my_tensors, geo: dict, world: int):
+    """``NVRX_B200_EXCHANGE=stream`` (opt-in, not yet run on a B200): the exchange leaves the training stream.
+
+    The fused / one-shot variants keep an exchange buffer of F x S bytes in HBM (F = clique size, S = snapshot) and run the
+    NVLink transfer on the training stream.  Here only the pack does (5 ms for 16 GB, which is what makes the snapshot
+    consistent); the packed buffer then travels in chunks, in the background:
+
+        comm stream :  all_gather_into_tensor(ring[c % 2], my staging[chunk c])       NVLink, F x chunk bytes of HBM per half
+        drain stream:  ring[c % 2][member r] -> host slot [r * slice + chunk c]        PCIe, starts when chunk c has arrived
+
+    HBM need: S (own staging, as for an unreplicated save) + 2 x F x chunk instead of F x S; the host slot and everything
+    behind it (views, writer, files) are the same as for the one-shot exchange."""
+    from .engine import Stream, stream_wait_event
+
+    layouts, slot_bytes = geo["layouts"], geo["slot_bytes"]
+    me, dev = group.my_group_rank, engine.device
+    plan = engine._plan_for(my_tensors, [False] * len(my_tensors))
+    assert list(plan.offsets) == layouts[me][0] and plan.staging_bytes == layouts[me][2]
+    staging = engine._ensure_staging(slot_bytes)  # padded to the clique-wide slice size: equal-sized all-gathers
+    stream = engine._current_stream()
+    if engine._staging_free is not None:
+        stream_wait_event(stream, engine._staging_free)
+    plan.pack(staging.ptr, stream)
+    engine.launches += 1 if plan.n_tiles else 0
+    packed = Event(dev)
+    packed.record(stream)
+
+    chunk = max(512, min(STREAM_CHUNK, slot_bytes) // 512 * 512)
+    n_chunks = -(-slot_bytes // chunk)
+    ring = getattr(engine, "_ring_buf", None)
+    if ring is None or ring.nbytes < 2 * world * chunk:
+        if ring is not None:
+            engine._side.synchronize()
+            ring.close()
+        ring = engine._ring_buf = DeviceBuffer(2 * world * chunk, dev)
+    if getattr(engine, "_comm", None) is None:
+        engine._comm = Stream(dev)
+    comm, drain = engine._comm, engine._side
+    comm.wait_event(packed)
+    torch_comm = torch.cuda.ExternalStream(comm.handle, device=torch.device("cuda", dev))
+
+    total = world * slot_bytes
+    slot = engine._acquire_slot(total)
+    base, sent = slot.drained_total, 0
+    half_free = [None, None]  # per ring half: recorded after its drains, the next all-gather into it waits for that
+    for c in range(n_chunks):
+        lo = c * chunk
+        ln = min(chunk, slot_bytes - lo)
+        half = ring.ptr + (c % 2) * world * chunk
+        if half_free[c % 2] is not None:
+            comm.wait_event(half_free[c % 2])
+        if world > 1:
+            with torch.cuda.stream(torch_comm):
+                dist.all_gather_into_tensor(as_uint8_tensor(half, world * ln, dev), as_uint8_tensor(staging.ptr + lo, ln, dev), group=group.group)
+            arrived = Event(dev)
+            arrived.record(comm.handle)
+            drain.wait_event(arrived)
+            src0 = half
+        else:
+            drain.wait_event(packed)
+            src0 = staging.ptr + lo
+        for r in range(world):
+            last = c == n_chunks - 1 and r == world - 1
+            check(
+                engine.lib.nvrx_drain(
+                    slot.buf.data_ptr + r * slot_bytes + lo, src0 + r * ln, ln, engine.drain_chunk, slot.buf.progress_ptr, base + sent,
+                    drain.handle, slot.done_event.handle if last else None,
+                ),
+                "nvrx_drain",
+            )
+            sent += ln
+        freed = Event(dev)
+        freed.record(drain.handle)
+        half_free[c % 2] = freed
+    assert sent == total
+    slot.drained_total = base + total
+    engine._staging_free = slot.done_event  # the last drain follows the last all-gather, which was the last reader of staging
+    engine._exchange_free = slot.done_event
+    engine.last_exchange = "nccl-streamed"
+    return _views_of_exchange_slot(engine, geo, slot)
+
+
 def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders, target_device):
     """See module docstring.  ``all_placeholders[r]`` describes rank r's tensors (already all-gathered).
 
@@ -247,6 +332,8 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
     container = to_host and _container_exchange(engine, group, world)
     geo = _geometry(group, all_placeholders, align, world, container)
     layouts, slot_bytes = geo["layouts"], geo["slot_bytes"]
+    if to_host and not container and _exchange_mode() == "stream":
+        return _allgather_streamed(engine, group, my_tensors, geo, world)
 
     plan = engine._plan_for(my_tensors, [False] * len(my_tensors), container)
     assert list(plan.offsets) == layouts[me][0] and plan.staging_bytes == layouts[me][2]
@@ -302,7 +389,12 @@ def allgather_packed(group, my_tensors: Sequence[torch.Tensor], all_placeholders
     )
     slot.drained_total = base + total
     engine._exchange_free = slot.done_event
+    return _views_of_exchange_slot(engine, geo, slot)
 
+
+def _views_of_exchange_slot(engine: SnapshotEngine, geo: dict, slot):
+    """Per-member host views of a slot that receives (or received) every member's slice, plus the Snapshot handle."""
+    dev_lists = geo["dev_lists"]
     # host views of a (slot buffer, structure) pair are built once: 4 us per tensor is 50 ms for 8 x 1455 tensors otherwise
     views = slot.__dict__.get("_exchange_views")
     if views is None or views[0] != slot.buf.name or views[1] is not dev_lists:

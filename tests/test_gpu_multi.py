@@ -53,7 +53,7 @@ def _w_allgather_batch(rank, world, mode):
     launches0 = SnapshotEngine.get().launches
     got = gw.all_gather_batch(mine, target_device="cpu")
     assert SnapshotEngine.get().launches == launches0 + 1  # ONE pack kernel; the reference does world*N broadcasts
-    assert SnapshotEngine.get().last_exchange == ("nccl-allgather" if mode == "nccl" else "p2p-fused")
+    assert SnapshotEngine.get().last_exchange == {"nccl": "nccl-allgather", "p2p": "p2p-fused", "stream": "nccl-streamed"}[mode]
     for s in gw.last_snapshots:
         s.wait()
     assert len(got) == world
@@ -69,6 +69,24 @@ def _w_allgather_batch(rank, world, mode):
     for r in range(world):
         for a, b in zip(got[r], flat_tensors(rank_state(r))):
             assert a.is_cuda and bit_equal(a, b)
+
+
+_UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="not yet validated on a B200")
+
+
+def _w_allgather_streamed_small_chunks(rank, world):
+    import os
+
+    os.environ["NVRX_B200_STREAM_CHUNK_MB"] = "0"  # -> 512-byte chunks: many ring turns even for the small test state
+    _w_allgather_batch(rank, world, "stream")
+
+
+@_UNVALIDATED
+def test_all_gather_batch_streamed_exchange(built_library):
+    """NVRX_B200_EXCHANGE=stream: pack on the training stream, chunked all-gather + drain in the background."""
+    world = min(torch.cuda.device_count(), 8)
+    run_ranks(_w_allgather_batch, world, "stream", backend="nccl")
+    run_ranks(_w_allgather_streamed_small_chunks, world, backend="nccl", timeout=600)
 
 
 @pytest.mark.parametrize("mode", ["p2p", "nccl"])
