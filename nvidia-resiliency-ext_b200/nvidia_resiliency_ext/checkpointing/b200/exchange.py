@@ -234,6 +234,19 @@ def _land_per_member(engine: SnapshotEngine, geo: dict, xbuf, world: int):
 STREAM_CHUNK = int(os.environ.get("NVRX_B200_STREAM_CHUNK_MB", "256")) << 20
 
 
+def stream_schedule(slot_bytes: int, chunk_limit: int):
+    """``(chunk, [(offset, length, ring half), ...])`` for moving ``slot_bytes`` of every member through the two ring halves:
+    chunks are multiples of 512 bytes (the last one may be shorter), alternate between the halves and cover the slice once."""
+    chunk = max(512, min(chunk_limit, slot_bytes) // 512 * 512)
+    steps = []
+    lo = 0
+    while lo < slot_bytes:
+        ln = min(chunk, slot_bytes - lo)
+        steps.append((lo, ln, len(steps) % 2))
+        lo += ln
+    return chunk, steps
+
+
 def _allgather_streamed(engine: SnapshotEngine, group, my_tensors, geo: dict, world: int):
     """``NVRX_B200_EXCHANGE=stream`` (opt-in, not yet run on a B200): the exchange leaves the training stream.
 
@@ -261,8 +274,7 @@ def _allgather_streamed(engine: SnapshotEngine, group, my_tensors, geo: dict, wo
     packed = Event(dev)
     packed.record(stream)
 
-    chunk = max(512, min(STREAM_CHUNK, slot_bytes) // 512 * 512)
-    n_chunks = -(-slot_bytes // chunk)
+    chunk, steps = stream_schedule(slot_bytes, STREAM_CHUNK)
     ring = getattr(engine, "_ring_buf", None)
     if ring is None or ring.nbytes < 2 * world * chunk:
         if ring is not None:
@@ -279,12 +291,10 @@ def _allgather_streamed(engine: SnapshotEngine, group, my_tensors, geo: dict, wo
     slot = engine._acquire_slot(total)
     base, sent = slot.drained_total, 0
     half_free = [None, None]  # per ring half: recorded after its drains, the next all-gather into it waits for that
-    for c in range(n_chunks):
-        lo = c * chunk
-        ln = min(chunk, slot_bytes - lo)
-        half = ring.ptr + (c % 2) * world * chunk
-        if half_free[c % 2] is not None:
-            comm.wait_event(half_free[c % 2])
+    for c, (lo, ln, h) in enumerate(steps):
+        half = ring.ptr + h * world * chunk
+        if half_free[h] is not None:
+            comm.wait_event(half_free[h])
         if world > 1:
             with torch.cuda.stream(torch_comm):
                 dist.all_gather_into_tensor(as_uint8_tensor(half, world * ln, dev), as_uint8_tensor(staging.ptr + lo, ln, dev), group=group.group)
@@ -296,7 +306,7 @@ def _allgather_streamed(engine: SnapshotEngine, group, my_tensors, geo: dict, wo
             drain.wait_event(packed)
             src0 = staging.ptr + lo
         for r in range(world):
-            last = c == n_chunks - 1 and r == world - 1
+            last = c == len(steps) - 1 and r == world - 1
             check(
                 engine.lib.nvrx_drain(
                     slot.buf.data_ptr + r * slot_bytes + lo, src0 + r * ln, ln, engine.drain_chunk, slot.buf.progress_ptr, base + sent,
@@ -307,7 +317,7 @@ def _allgather_streamed(engine: SnapshotEngine, group, my_tensors, geo: dict, wo
             sent += ln
         freed = Event(dev)
         freed.record(drain.handle)
-        half_free[c % 2] = freed
+        half_free[h] = freed
     assert sent == total
     slot.drained_total = base + total
     engine._staging_free = slot.done_event  # the last drain follows the last all-gather, which was the last reader of staging

@@ -102,3 +102,18 @@ def test_published_slot_loads_back_for_any_mix_of_tensors(built_library, shm_dir
         hb.close()
         if target.exists():
             target.unlink()
+
+
+@settings(**SETTINGS)
+@given(slot_kib=st.integers(1, 5000), limit=st.sampled_from([0, 512, 4096, 1 << 20, 256 << 20]), odd=st.integers(0, 1))
+def test_stream_schedule_covers_the_slice_once(slot_kib, limit, odd):
+    from nvidia_resiliency_ext.checkpointing.b200.exchange import stream_schedule
+
+    slot_bytes = slot_kib * 1024 - odd * 512  # slices are multiples of 512 bytes
+    chunk, steps = stream_schedule(slot_bytes, limit)
+    assert chunk % 512 == 0 and chunk >= 512
+    pos = 0
+    for i, (lo, ln, half) in enumerate(steps):
+        assert lo == pos and 0 < ln <= chunk and half == i % 2
+        pos += ln
+    assert pos == slot_bytes and all(ln == chunk for _, ln, _ in steps[:-1])
