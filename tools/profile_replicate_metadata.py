@@ -39,7 +39,8 @@ def job(rank, world, iters, manager=False):
 
         from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
 
-        mgr = LocalCheckpointManager(tempfile.mkdtemp(prefix="nvrx_prof_", dir="/dev/shm"), repl_strategy=strat)
+        tmp_root = tempfile.mkdtemp(prefix="nvrx_prof_", dir="/dev/shm")
+        mgr = LocalCheckpointManager(tmp_root, repl_strategy=strat)
         for it in range(iters):
             sd = c2_like_state(rank)
             sd["iteration"] = it
@@ -66,7 +67,7 @@ def job(rank, world, iters, manager=False):
         import shutil
 
         dist.barrier()
-        shutil.rmtree(mgr.local_ckpt_dir, ignore_errors=True)
+        shutil.rmtree(tmp_root, ignore_errors=True)
         return
     for it in range(iters):
         sd = c2_like_state(rank)
