@@ -93,3 +93,8 @@ if [[ $WHAT == all || $WHAT == ncu ]]; then
       python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1
   tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/
 fi
+if [[ $WHAT == ncu_crc ]]; then
+  NCU_REPS=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:crc_chunks -c 2 -f -o gpurun_out/prof_crc \
+      python tools/ncu_target.py > gpurun_out/ncu_crc.log 2>&1
+  tail -3 gpurun_out/ncu_crc.log; ls -la gpurun_out/
+fi

@@ -1,5 +1,7 @@
-"""Small launch sequence for ncu: the C2 state, then pack (TMA walker), pack (LDG walker), scatter, narrow pack.
-Usage under ncu:  ncu --set full -k regex:walk_ -c 6 -o gpurun_out/prof python tools/ncu_target.py"""
+"""Small launch sequence for ncu: the C2 state, then pack (TMA walker), pack (LDG walker), scatter, narrow pack, and the
+checksum kernel in both table layouts (NCU_CRC=0 skips it).
+Usage under ncu:  ncu --set full -k regex:walk_ -c 6 -o gpurun_out/prof python tools/ncu_target.py
+                  ncu --set full -k regex:crc_chunks -c 2 -o gpurun_out/prof_crc python tools/ncu_target.py"""
 import os
 import sys
 
@@ -33,4 +35,16 @@ for _ in range(reps):
 for _ in range(reps):
     narrow.scatter(stg.ptr, st)
 torch.cuda.synchronize()
+if os.environ.get("NCU_CRC", "1") != "0":
+    from nvidia_resiliency_ext.checkpointing.b200.engine import CrcPlan  # noqa: E402
+
+    plan.set_variant(2)
+    plan.pack(stg.ptr, st)
+    crc = CrcPlan(plan.offsets, plan.packed_nbytes, 0)
+    values = torch.zeros(crc.n_values + 2, dtype=torch.int32).pin_memory()
+    for variant in ("private", "shared"):
+        os.environ["NVRX_B200_CRC_VARIANT"] = variant
+        for _ in range(reps):
+            crc.run(stg.ptr, values.data_ptr(), 0, 0, st)
+    torch.cuda.synchronize()
 print("ncu target done", total)
