@@ -3,6 +3,7 @@ import os
 import threading
 import time
 import zlib
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -230,5 +231,28 @@ def test_readv_fd_fills_the_slot_from_a_file(built_library, tmp_path):
                 hb.readv_fd([hb.capacity - 5], [100], [0], fd, threads=2)
         finally:
             os.close(fd)
+    finally:
+        hb.close()
+
+
+def test_writev_fd_with_preallocation(built_library, tmp_path, monkeypatch):
+    """NVRX_B200_WRITE_FALLOCATE=1 (opt-in): same bytes in the file, destination pages allocated by one fallocate call."""
+    monkeypatch.setenv("NVRX_B200_WRITE_FALLOCATE", "1")
+    rng = np.random.default_rng(2)
+    hb = make_hb(24 << 20)
+    try:
+        payload = rng.integers(0, 256, 24 << 20, dtype=np.uint8)
+        hb.as_tensor(24 << 20).numpy()[:] = payload
+        offs, sizes, file_offs = [0, 9 << 20, (20 << 20) + 3], [5 << 20, 10 << 20, 1000], [4096, 6 << 20, 17 << 20]
+        for path in (tmp_path / "disk.bin", Path("/dev/shm") / f"nvrx_falloc_{os.getpid()}.bin"):
+            fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o644)
+            try:
+                hb.writev_fd(offs, sizes, file_offs, fd, threads=4)
+                got = np.fromfile(path, dtype=np.uint8)
+                for o, n, f in zip(offs, sizes, file_offs):
+                    assert np.array_equal(got[f : f + n], payload[o : o + n])
+            finally:
+                os.close(fd)
+                os.unlink(path)
     finally:
         hb.close()

@@ -41,6 +41,7 @@ if [[ $WHAT == zerocopy ]]; then
   guarded timeout 600 python tools/crc_bench.py --gb 2 > gpurun_out/crc_bench.jsonl 2> gpurun_out/crc_bench.err
   guarded timeout 600 python tools/crc_bench.py --gb 16 >> gpurun_out/crc_bench.jsonl 2>> gpurun_out/crc_bench.err; cat gpurun_out/crc_bench.jsonl
   guarded timeout 900 python bench.py > gpurun_out/bench_copy.json 2> gpurun_out/bench_copy.err; cat gpurun_out/bench_copy.json
+  NVRX_B200_WRITE_FALLOCATE=1 guarded timeout 900 python bench.py > gpurun_out/bench_fallocate.json 2> gpurun_out/bench_fallocate.err; cat gpurun_out/bench_fallocate.json
   NVRX_B200_RESTORE_PREAD=1 guarded timeout 900 python bench.py > gpurun_out/bench_pread.json 2> gpurun_out/bench_pread.err; cat gpurun_out/bench_pread.json
   NVRX_B200_ZERO_COPY=1 NVRX_B200_GPU_CRC=1 guarded timeout 900 python bench.py > gpurun_out/bench_zerocopy.json 2> gpurun_out/bench_zerocopy.err; tail -3 gpurun_out/bench_zerocopy.err; cat gpurun_out/bench_zerocopy.json
 fi
