@@ -199,3 +199,50 @@ def test_dcp_writer_cuda_branch(monkeypatch, built_library, tmp_path, dist_1rank
         got = {"model": {k: torch.zeros_like(v) for k, v in host_state["model"].items()}, "opt": {"step": torch.tensor(0), "lr": None}}
         dcp.load(got, storage_reader=FileSystemReader(tmp_path / "async"))
         assert torch.equal(got["model"]["w"], host_state["model"]["w"]) and got["opt"]["lr"] == 0.5
+
+
+@pytest.mark.parametrize("persistent", [True, False])
+def test_default_paths_torch_async_and_local_manager(monkeypatch, built_library, shm_dir, tmp_path, dist_1rank, persistent):
+    """No switches set: the copying writer, slot release on finalize, cleanup of older iterations, gather-based restore."""
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
+    from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+    from nvidia_resiliency_ext.checkpointing.utils import preload_tensors
+
+    for var in ("NVRX_B200_ZERO_COPY", "NVRX_B200_GPU_CRC", "NVRX_B200_VERIFY_RESTORE", "NVRX_B200_RESTORE_PREAD"):
+        monkeypatch.delenv(var, raising=False)
+    with fake_device(monkeypatch) as (engine, lib):
+        ckpt = TorchAsyncCheckpoint(persistent_queue=persistent)
+        try:
+            for i in range(3):
+                path = shm_dir / f"plain{i}.pt"
+                ckpt.async_save(_state(i), path)
+                ckpt.finalize_async_save(blocking=True)
+                assert os.stat(path).st_nlink == 1  # a copy, not a link
+                _same(torch.load(path, weights_only=False), _state(i, wrap=False))
+            assert len(engine._slots) == 2 and not any(s.busy for s in engine._slots)
+        finally:
+            ckpt.close()
+        host, snap = preload_tensors(_state(7), non_blocking=True, return_snapshot=True)
+        snap.wait()
+        _same(host, _state(7, wrap=False))
+        snap.release()
+
+        mgr = LocalCheckpointManager(tmp_path / "ckpt")
+        q = AsyncCallsQueue(persistent=False)
+        try:
+            for it in (1, 2):
+                req = mgr.save(BasicTensorAwareStateDict(_state(20 + it)), it, is_async=True)
+                q.schedule_async_request(req)
+                q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+            import time
+
+            time.sleep(0.5)  # cleanup of iteration 1 runs in a background thread
+            assert sorted(p.name for p in mgr.local_ckpt_dir.iterdir()) == ["iter_0000002_0_local.pt"]
+            assert mgr.find_latest() == 2
+            loaded, _ = mgr.load()
+            _same(loaded.state_dict, _state(22, wrap=False))
+            assert all(t.is_cuda for t in loaded.tensors) and engine.resident_restores == 0
+        finally:
+            q.close()
