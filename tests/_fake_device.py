@@ -205,6 +205,7 @@ def fake_device(monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(eng.SnapshotEngine, "_current_stream", lambda self: 0)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self if isinstance(self, FakeCudaTensor) else FakeCudaTensor.wrap(self))
     real_empty = torch.empty
 
     def empty(*args, **kwargs):

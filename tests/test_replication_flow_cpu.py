@@ -104,3 +104,68 @@ def test_replicated_save_lose_a_rank_and_restore(shm_dir, built_library, mode, z
 
 def test_replicated_three_members_streamed(shm_dir, built_library):
     run_ranks(_worker, 3, str(shm_dir), "stream", False, (0, 2), timeout=300)
+
+
+def _sharded_worker(rank, world, root, kill):
+    import time
+
+    import torch.distributed as dist
+
+    from _fake_device import FakeCudaTensor, fake_device, plain
+    from oracle import snapshot_oracle as orc
+
+    os.environ["NVRX_B200_EXCHANGE"] = "nccl"
+    mp = pytest.MonkeyPatch()
+    try:
+        with fake_device(mp) as (engine, lib):
+            import ctypes as C
+
+            from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+            from nvidia_resiliency_ext.checkpointing.b200 import exchange as xch
+            from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+            from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.sharded_local_manager import ShardedLocalCheckpointManager
+
+            def host_bytes(ptr, nbytes, device):
+                return torch.frombuffer((C.c_uint8 * max(nbytes, 1)).from_address(ptr), dtype=torch.uint8)[:nbytes]
+
+            class _S:
+                cuda_stream = 0
+
+                def synchronize(self):
+                    pass
+
+            mp.setattr(xch, "as_uint8_tensor", host_bytes)
+            mp.setattr(torch.cuda, "current_stream", lambda *a, **k: _S())
+            mp.setattr(torch.cuda, "device_count", lambda: 1)
+            mgr = ShardedLocalCheckpointManager.from_replication_params(root, replication_jump=1, replication_factor=world)
+            q = AsyncCallsQueue(persistent=False)
+            for it in (1, 2):
+                req = mgr.save(BasicTensorAwareStateDict(_rank_state(rank + 10 * it, FakeCudaTensor.wrap)), it, is_async=True)
+                q.schedule_async_request(req)
+                q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+            time.sleep(0.5)
+            n = world - 1
+            files = sorted(p.name for p in mgr.local_ckpt_dir.iterdir())
+            want = [f"iter_0000002_{rank}_local.pt"] + [f"iter_0000002_{m}_local.s{mgr._others(m).index(rank)}of{n}.pt" for m in range(world) if m != rank]
+            assert files == sorted(want), (files, want)
+            dist.barrier()
+            if rank in kill:
+                for p in mgr.local_ckpt_dir.iterdir():
+                    p.unlink()
+            dist.barrier()
+            mgr2 = ShardedLocalCheckpointManager(root, clique=mgr.clique)
+            assert mgr2.find_latest() == 2
+            loaded, cid = mgr2.load()
+            want_t = orc.flatten_tensors(_rank_state(rank + 20, None))
+            got = list(loaded.tensors)
+            assert cid == (2, rank, "") and len(got) == len(want_t)
+            assert all(a.is_cuda and a.dtype == b.dtype and torch.equal(plain(a), b) for a, b in zip(got, want_t))
+            q.close()
+    finally:
+        mp.undo()
+
+
+@pytest.mark.parametrize("world,kill", [(2, (1,)), (3, (0,))])
+def test_striped_replicas_rebuild_a_lost_member(shm_dir, built_library, world, kill):
+    """ShardedLocalCheckpointManager's device branch (pack + all_to_all of fragments, rebuild by all-gathering them back)."""
+    run_ranks(_sharded_worker, world, str(shm_dir), kill, timeout=300)
