@@ -246,3 +246,32 @@ def test_default_paths_torch_async_and_local_manager(monkeypatch, built_library,
             assert all(t.is_cuda for t in loaded.tensors) and engine.resident_restores == 0
         finally:
             q.close()
+
+
+def test_abort_gives_host_slots_back(monkeypatch, built_library, shm_dir, dist_1rank):
+    """In-process restart: aborted saves never finalize; their pinned slots must come back or the pool runs dry."""
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue, AsyncRequest, abort_nvrx_checkpoint
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import save_state_dict_async_plan
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
+
+    with fake_device(monkeypatch) as (engine, lib):
+        ckpt = TorchAsyncCheckpoint(persistent_queue=True)
+        q = AsyncCallsQueue(persistent=True)
+        try:
+            for round_ in range(3):  # three saves per round: more than the pool has slots
+                ckpt.async_save(_state(round_), shm_dir / f"a{round_}.pt")
+                dev_state = {"m": {"w": FakeCudaTensor.wrap(torch.randn(100, 10))}}
+                writer = FileSystemWriterAsync(shm_dir / f"dcp{round_}", thread_count=1)
+                save_state_dict_async_plan(dev_state, writer, None, 0)
+                save_fn, preload_fn, save_args = writer.get_save_function_and_args()
+                q.schedule_async_request(AsyncRequest(save_fn, save_args, [], preload_fn=preload_fn))
+                abort_nvrx_checkpoint()
+                del writer  # the aborted DCP save never reaches retrieve_write_results
+                ckpt.async_save(_state(100 + round_), shm_dir / f"b{round_}.pt")  # works again right away
+                ckpt.finalize_async_save(blocking=True)
+                _same(torch.load(shm_dir / f"b{round_}.pt", weights_only=False), _state(100 + round_, wrap=False))
+            assert len(engine._slots) <= engine.max_host_slots and not any(s.busy for s in engine._slots)
+        finally:
+            ckpt.close()
+            q.close()
