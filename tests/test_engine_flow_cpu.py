@@ -275,3 +275,24 @@ def test_abort_gives_host_slots_back(monkeypatch, built_library, shm_dir, dist_1
         finally:
             ckpt.close()
             q.close()
+
+
+def test_warmup_creates_the_resources_of_the_first_save(monkeypatch, built_library, shm_dir, dist_1rank):
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
+
+    with fake_device(monkeypatch) as (engine, lib):
+        ckpt = TorchAsyncCheckpoint(persistent_queue=False)
+        try:
+            sd = _state(3)
+            nbytes = ckpt.warmup(sd)
+            assert nbytes > 0 and engine._staging is not None and engine._staging.nbytes >= nbytes
+            bufs = [s.buf.name for s in engine._slots]
+            assert all(s.buf is not None and s.buf.capacity >= nbytes and not s.busy for s in engine._slots)
+            plans = len(engine._plans)
+            ckpt.async_save(sd, shm_dir / "w.pt")
+            ckpt.finalize_async_save(blocking=True)
+            assert [s.buf.name for s in engine._slots] == bufs and len(engine._plans) == plans  # nothing new was allocated
+            _same(torch.load(shm_dir / "w.pt", weights_only=False), _state(3, wrap=False))
+            assert ckpt.warmup({"x": torch.ones(3)}) == 0  # host state: nothing to prepare
+        finally:
+            ckpt.close()
