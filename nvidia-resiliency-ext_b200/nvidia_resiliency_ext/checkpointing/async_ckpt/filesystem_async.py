@@ -37,7 +37,6 @@ from typing import Callable, Dict, List, Optional, Tuple, Union
 import torch
 from torch import multiprocessing as mp
 from torch.distributed.checkpoint import FileSystemWriter
-from torch.distributed.checkpoint.metadata import Metadata
 from torch.distributed.checkpoint.planner import SavePlan, SavePlanner, WriteItem, WriteItemType
 from torch.distributed.checkpoint.storage import WriteResult
 from torch.distributed.checkpoint.utils import _is_wrapped_exception, _wrap_exception
@@ -280,11 +279,35 @@ class FileSystemWriterAsync(FileSystemWriter):
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         return dataclasses.replace(local_plan, storage_data=_StoragePrefix(f"__{rank}_"))
 
-    def finish(self, metadata: Metadata, results: List[List[WriteResult]]) -> None:
-        # plans cached inside the metadata by the saver are not part of the on-disk format
-        if hasattr(metadata, "all_local_plans"):
-            metadata.all_local_plans = None
+    def finish(self, metadata, results: List[List[WriteResult]]) -> None:
+        """Coordinator: write ``.metadata``.  The saver hangs every rank's local plan on the metadata object
+        (``all_local_plans``) so that a job resuming from this checkpoint can skip the plan exchange; recent PyTorch copies the
+        dataclass inside ``finish`` (``dataclasses.replace``) and loses such extra attributes, so they are put back into the
+        written file (small, atomic rewrite).  Readers that do not know the attribute ignore it."""
+        plans = getattr(metadata, "all_local_plans", None)
         super().finish(metadata, results)
+        if plans is None:
+            return
+        import pickle
+
+        path = os.path.join(os.fspath(self.checkpoint_dir), ".metadata")
+        try:
+            with open(path, "rb") as fh:
+                written = pickle.load(fh)  # nosec B301 - the file this process has just written
+            if getattr(written, "all_local_plans", None) is None:
+                written.all_local_plans = plans
+                tmp = path + f".plans{os.getpid()}"
+                with open(tmp, "wb") as fh:
+                    pickle.dump(written, fh)
+                os.replace(tmp, path)
+        except OSError as exc:  # the checkpoint is complete without it; only the resume shortcut is lost
+            logger.warning(f"could not store the local plans in {path}: {exc}")
+
+    @staticmethod
+    def preload_tensors(payload, non_blocking: bool = True):
+        """Kept for API compatibility (reference ``:563``): there the D2H of the write items happens here; in this
+        implementation it was enqueued by ``prepare_write_data`` already, so the payload passes through."""
+        return payload
 
     @property
     def checkpoint_id(self) -> Union[str, os.PathLike]:

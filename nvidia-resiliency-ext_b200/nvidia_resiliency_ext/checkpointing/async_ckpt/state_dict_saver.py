@@ -1,8 +1,9 @@
 """Planning and finalization halves of an asynchronous ``torch.distributed.checkpoint`` save.
 
 Mirrors the entry points of reference ``checkpointing/async_ckpt/state_dict_saver.py`` (``save_state_dict_async_plan`` ``:236``,
-``save_state_dict_async_finalize`` ``:417``, ``CheckpointMetadataCache`` ``:52``, ``init_checkpoint_metadata_cache`` ``:212``):
-planning (collective) -> ``storage_writer.prepare_write_data`` (stages the tensors; here: one pack kernel + drain) -> the
+``save_state_dict_async_finalize`` ``:417``, ``CheckpointMetadataCache`` ``:52``, ``init_checkpoint_metadata_cache`` ``:212``, ``verify_global_md_reuse`` ``:374``):
+planning (collective; three ways, cheapest first: reuse the cached plan / decentralized planning with a gather only for the
+metadata, or none at all when the plans stored in the loaded checkpoint still match / full reduce_scatter) -> ``storage_writer.prepare_write_data`` (stages the tensors; here: one pack kernel + drain) -> the
 caller schedules the write -> ``save_state_dict_async_finalize`` gathers write results and lets the coordinator write
 ``.metadata``.  The optional cache skips the plan exchange when every rank's local plan is unchanged since the last save.
 """
@@ -36,6 +37,7 @@ class CheckpointMetadataCache:
         self.cached_local_plan: Optional[SavePlan] = None
         self.cached_global_metadata: Optional[Metadata] = None
         self.validated_cache_reuse: bool = False
+        self.validated_loaded_metadata_reuse: bool = False  # the plans stored in the loaded checkpoint still match ours
         self.loaded_all_plans: Optional[List[SavePlan]] = None
 
     def set_cached_global_metadata(self, cached_global_metadata: Optional[Metadata]):
@@ -46,7 +48,8 @@ class CheckpointMetadataCache:
     def get_cache_metadata(self):
         return self.cached_central_plan, self.cached_local_plan, self.validated_cache_reuse, self.loaded_all_plans
 
-    def set_cache_metadata(self, central_plan: SavePlan, local_plan: SavePlan, unchanged: bool):
+    def set_cache_metadata(self, central_plan: SavePlan, local_plan: SavePlan, unchanged: bool, loaded_reuse: bool = False):
+        self.validated_loaded_metadata_reuse = loaded_reuse
         self.validated_cache_reuse = unchanged and self.cached_central_plan is not None
         self.cached_central_plan = central_plan
         self.cached_local_plan = local_plan
@@ -55,14 +58,16 @@ class CheckpointMetadataCache:
         """On the coordinator keep the freshest global metadata and substitute the cached one when planning was skipped."""
         writer, metadata, dist_wrapper = ret
         if rank == coordinator_rank:
-            if metadata is None:
+            if metadata is None:  # planning was skipped (cached plan) or needed no metadata exchange (loaded plans match)
                 metadata = self.cached_global_metadata
             else:
                 self.cached_global_metadata = metadata
         return writer, metadata, dist_wrapper
 
     def get_metadata_caching_status(self):
-        return {"validated_cache_reuse": self.validated_cache_reuse, "has_central_plan": self.cached_central_plan is not None,
+        return {"validated_cache_reuse": self.validated_cache_reuse,
+                "validated_loaded_metadata_reuse": self.validated_loaded_metadata_reuse,
+                "has_central_plan": self.cached_central_plan is not None,
                 "has_global_metadata": self.cached_global_metadata is not None}
 
 
@@ -87,6 +92,23 @@ def _plans_equal(a: Optional[SavePlan], b: Optional[SavePlan]) -> bool:
     if a is None or b is None:
         return False
     return all(getattr(a, f.name) == getattr(b, f.name) for f in fields(a) if f.name != "storage_data")
+
+
+def _compare_dataclasses(a, b) -> List[str]:
+    """Names of the fields in which two plans differ (debug output of the reuse checks)."""
+    return [f.name for f in fields(a) if getattr(a, f.name, None) != getattr(b, f.name, None)]
+
+
+def verify_global_md_reuse(loaded_all_plans: Optional[List[SavePlan]], local_plan: SavePlan, rank: int, dist_wrapper: _DistWrapper) -> bool:
+    """Can the global metadata loaded with the checkpoint we resumed from be written again as it is?  Yes when that
+    checkpoint stored one local plan per rank of this job and every rank's new local plan equals its stored one (storage
+    prefixes aside).  Collective when plans were loaded (one small all_reduce)."""
+    if not loaded_all_plans or len(loaded_all_plans) != dist_wrapper.get_world_size():
+        return False
+    mine = _plans_equal(local_plan, loaded_all_plans[rank])
+    if not mine:
+        logger.debug(f"rank {rank}: local plan differs from the loaded one in {_compare_dataclasses(local_plan, loaded_all_plans[rank])}")
+    return _all_ranks_agree(mine, dist_wrapper)
 
 
 def _all_ranks_agree(flag: bool, dist_wrapper: _DistWrapper) -> bool:
@@ -121,12 +143,22 @@ def save_state_dict_async_plan(
     storage_writer.set_up_storage_writer(dist_wrapper.is_coordinator)
     local_plan = storage_writer.prepare_local_plan(planner.create_local_plan())
 
-    unchanged = False
+    unchanged = loaded_reuse = False
     if cache is not None:
         unchanged = _all_ranks_agree(_plans_equal(local_plan, cache.cached_local_plan), dist_wrapper)
     if unchanged and cache.cached_central_plan is not None:
         logger.debug(f"rank: {rank}, reusing the cached plan")
         central_plan = cache.cached_central_plan  # global metadata comes from the cache on the coordinator
+    elif getattr(planner, "can_run_decentralized_global_plan", False) and getattr(storage_writer, "can_run_decentralized_global_plan", False):
+        # every rank finishes its own plan; the plans travel (gather, not scatter) only because the coordinator needs them for
+        # the global metadata -- and not even that when the checkpoint we resumed from already holds matching ones
+        loaded_reuse = verify_global_md_reuse(cache.loaded_all_plans if cache is not None else None, local_plan, rank, dist_wrapper)
+        if not loaded_reuse:
+            all_local_plans = dist_wrapper.gather_object(local_plan)
+            if dist_wrapper.is_coordinator:
+                _, global_metadata = planner.create_global_plan(all_local_plans)
+                global_metadata.all_local_plans = all_local_plans  # stored in .metadata: lets a resumed job skip this gather
+        central_plan = storage_writer.prepare_decentralized_global_plan(planner.create_decentralized_global_plan(local_plan))
     else:
         def global_step(all_local_plans):
             nonlocal global_metadata
@@ -142,7 +174,7 @@ def save_state_dict_async_plan(
     logger.debug(f"rank: {rank}, write(async) time: {time() - t1}")
     ret = (storage_writer, global_metadata, dist_wrapper)
     if cache is not None:
-        cache.set_cache_metadata(central_plan, local_plan, unchanged)
+        cache.set_cache_metadata(central_plan, local_plan, unchanged, loaded_reuse)
         ret = cache.prepare_save_state_dict_ret(rank, coordinator_rank, ret)
     return ret
 

@@ -372,3 +372,63 @@ def test_abort_with_a_pending_dcp_save_and_resume(tmp_path, dist_1rank):
     finally:
         q_dcp.close()
         q_plain.close()
+
+
+class _DecentralPlanner(DefaultSavePlanner):
+    """A planner that finishes its plan on its own (what Megatron-Core's planner offers): every rank owns disjoint keys."""
+
+    can_run_decentralized_global_plan = True
+
+    def create_decentralized_global_plan(self, local_plan):
+        return local_plan
+
+
+def _decentral_job(rank, world, root):
+    import pickle
+
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.state_dict_saver import CheckpointMetadataCache
+
+    q = AsyncCallsQueue(persistent=False)
+    gathers = []
+    from torch.distributed.checkpoint.utils import _DistWrapper
+
+    real_gather = _DistWrapper.gather_object
+    _DistWrapper.gather_object = lambda self, obj: (gathers.append(type(obj).__name__), real_gather(self, obj))[1]
+
+    def save(step, cache):
+        state = {f"r{rank}": _state(rank, step)["model"]}
+        path = os.path.join(root, f"d{step}")
+        ret = _async_save(state, path, q, planner=_DecentralPlanner(), enable_cache=True, metadata_cache=cache)
+        q.maybe_finalize_async_calls(blocking=True)
+        dist.barrier()
+        got = {f"r{rank}": {k: torch.zeros_like(v) for k, v in state[f"r{rank}"].items()}}
+        dcp.load(got, storage_reader=FileSystemReader(path))
+        assert all(torch.equal(got[f"r{rank}"][k], v) for k, v in state[f"r{rank}"].items()), step
+        return path, ret
+
+    cache = CheckpointMetadataCache()
+    path0, ret0 = save(0, cache)
+    assert gathers.count("SavePlan") == 1  # plans gathered once for the metadata, never scattered
+    with open(os.path.join(path0, ".metadata"), "rb") as fh:
+        md = pickle.load(fh)
+    assert len(md.all_local_plans) == world  # stored for a job that resumes from this checkpoint
+    # "resume": a fresh cache seeded with the loaded metadata -> no plan exchange at all, the coordinator re-uses the metadata
+    resumed = CheckpointMetadataCache()
+    resumed.set_cached_global_metadata(md)
+    path1, ret1 = save(1, resumed)
+    assert gathers.count("SavePlan") == 1 and resumed.validated_loaded_metadata_reuse
+    assert (ret1[1] is not None) == (rank == 0)
+    # a changed structure is noticed by every rank: back to gathering
+    resumed2 = CheckpointMetadataCache()
+    resumed2.set_cached_global_metadata(md)
+    state = {f"r{rank}": dict(_state(rank, 2)["model"], extra=torch.ones(3 + rank))}
+    _async_save(state, os.path.join(root, "d2"), q, planner=_DecentralPlanner(), enable_cache=True, metadata_cache=resumed2)
+    q.maybe_finalize_async_calls(blocking=True)
+    assert gathers.count("SavePlan") == 2 and not resumed2.validated_loaded_metadata_reuse
+    _DistWrapper.gather_object = real_gather
+    q.close()
+
+
+def test_decentralized_planning_and_reuse_of_loaded_metadata(tmp_path):
+    run_ranks(_decentral_job, 2, str(tmp_path))
