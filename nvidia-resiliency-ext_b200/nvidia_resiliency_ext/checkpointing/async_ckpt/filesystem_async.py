@@ -49,6 +49,7 @@ WRAPPED_EXCEPTION = Tuple[BaseException, object]
 
 _results_queue = None
 _results_manager = None
+_live_saves: set = set()  # ids of saves of this process whose results have not been retrieved (or given up) yet
 
 
 def get_write_results_queue(mp_mode: str = "spawn"):
@@ -129,6 +130,7 @@ class FileSystemWriterAsync(FileSystemWriter):
         self.results_queue = None
         self._payload: Optional[dict] = None
         self._snapshot = None
+        self._save_id: Optional[str] = None
 
     # ---- stage 1 (trainer) ------------------------------------------------------------------------
     def prepare_write_data(self, plan: SavePlan, planner: SavePlanner) -> None:
@@ -177,12 +179,21 @@ class FileSystemWriterAsync(FileSystemWriter):
             return None, None, []
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.results_queue = get_write_results_queue()
-        save_fn = drain_aware(partial(self.write_preloaded_data, self._ctor, int(self.thread_count), self.separation_hint))
+        # the results queue is shared by every save of this process; a save that was aborted after its writer had reported
+        # leaves an entry behind that nobody asks for -- entries carry the id of their save so that it is never mistaken for
+        # the result of a later one
+        import uuid
+
+        self._save_id = uuid.uuid4().hex
+        _live_saves.add(self._save_id)
+        save_fn = drain_aware(
+            partial(self.write_preloaded_data, self._ctor, int(self.thread_count), self.separation_hint, self._save_id)
+        )
         return save_fn, partial(_passthrough, self._payload), [rank, None, self.results_queue]
 
     # ---- stage 2 (writer process) -------------------------------------------------------------------
     @staticmethod
-    def write_preloaded_data(ctor, thread_count: int, separation_hint, rank: int, payload: dict, results_queue) -> None:
+    def write_preloaded_data(ctor, thread_count: int, separation_hint, save_id, rank: int, payload: dict, results_queue) -> None:
         """Write the files of this rank with PyTorch's ``FileSystemWriter`` from staged host data; the outcome (list of
         ``WriteResult`` or a wrapped exception) is reported on ``results_queue``.  Errors are reported, not raised; only a
         ``SystemExit`` / ``KeyboardInterrupt`` (the worker is being aborted) passes through, without a report."""
@@ -222,7 +233,7 @@ class FileSystemWriterAsync(FileSystemWriter):
         finally:
             for hb in held:
                 hb.close(unlink=False)
-        results_queue.put((rank, outcome))
+        results_queue.put((rank, save_id, outcome))
 
     # ---- stage 3 (trainer) ------------------------------------------------------------------------
     def write_data(self, plan: SavePlan, planner: SavePlanner):
@@ -237,10 +248,13 @@ class FileSystemWriterAsync(FileSystemWriter):
             stash = []
             try:
                 while True:
-                    got_rank, outcome = self.results_queue.get(timeout=600)
-                    if got_rank == rank:
+                    got_rank, save_id, outcome = self.results_queue.get(timeout=600)
+                    if save_id == self._save_id:
                         break
-                    stash.append((got_rank, outcome))  # another writer instance of this process group: put it back
+                    if save_id in _live_saves:
+                        stash.append((got_rank, save_id, outcome))  # another save of this process still in flight: put it back
+                    else:
+                        logger.debug(f"rank {rank}: dropping the result of an abandoned save ({save_id})")
             except queue_mod.Empty:
                 return _wrap_exception(RuntimeError(f"rank {rank}: no results from the checkpoint writer"))
             finally:
@@ -256,13 +270,16 @@ class FileSystemWriterAsync(FileSystemWriter):
                 return _wrap_exception(RuntimeError(f"rank {rank}: the writer reported no results for a non-empty plan"))
             return outcome
         finally:
+            _live_saves.discard(self._save_id)
             if self._snapshot is not None:
                 self._snapshot.release()
                 self._snapshot = None
             self._payload = None
 
     def __del__(self):
-        # a save that was aborted (in-process restart) never reaches retrieve_write_results: give its host slot back
+        # a save that was aborted (in-process restart) never reaches retrieve_write_results: give its host slot back and mark
+        # whatever its writer may still report as nobody's
+        _live_saves.discard(getattr(self, "_save_id", None))
         snap, self._snapshot = getattr(self, "_snapshot", None), None
         if snap is not None:
             try:

@@ -220,9 +220,9 @@ def test_writer_process_reads_cuda_items_from_the_snapshot_slot(tmp_path, built_
         t = threading.Thread(target=drain)
         t.start()
         results = multiprocessing.get_context("spawn").Manager().Queue()
-        FileSystemWriterAsync.write_preloaded_data(writer._ctor, 1, None, 0, payload, results)
+        FileSystemWriterAsync.write_preloaded_data(writer._ctor, 1, None, "test-save", 0, payload, results)
         t.join()
-        rank, outcome = results.get(timeout=10)
+        rank, save_id, outcome = results.get(timeout=10)
         assert rank == 0 and isinstance(outcome, list) and len(outcome) == len(payload["plan"].items), outcome
         writer.finish(metadata, [outcome])
     finally:
@@ -341,7 +341,7 @@ def test_abort_with_a_pending_dcp_save_and_resume(tmp_path, dist_1rank):
     from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue, AsyncRequest, abort_nvrx_checkpoint
 
     state = _state()
-    q_dcp, q_plain = AsyncCallsQueue(persistent=True), AsyncCallsQueue(persistent=True)
+    q_dcp, q_plain = AsyncCallsQueue(persistent=True), AsyncCallsQueue(persistent=False)
     try:
         _async_save(state, tmp_path / "a", q_dcp)
         q_plain.schedule_async_request(AsyncRequest(torch.save, ({"x": torch.arange(4)}, tmp_path / "plain_a.pt"), []))
@@ -362,8 +362,7 @@ def test_abort_with_a_pending_dcp_save_and_resume(tmp_path, dist_1rank):
         q_plain.maybe_finalize_async_calls(blocking=True, no_dist=True)
         _loaded_equals(tmp_path / "b", _state())
         assert torch.equal(torch.load(tmp_path / "plain_b.pt")["x"], torch.arange(4))
-        for q in (q_dcp, q_plain):
-            assert q._get_async_caller()._debug_is_async_process_running() is True
+        assert q_dcp._get_async_caller()._debug_is_async_process_running() is True
 
         # an exception in the trainer right after scheduling, abort, then the queue object goes away
         _async_save(state, tmp_path / "c", q_dcp)
@@ -432,3 +431,31 @@ def _decentral_job(rank, world, root):
 
 def test_decentralized_planning_and_reuse_of_loaded_metadata(tmp_path):
     run_ranks(_decentral_job, 2, str(tmp_path))
+
+
+def test_result_of_an_abandoned_save_is_not_taken_for_the_next_one(tmp_path, dist_1rank):
+    """The write-results queue is process-wide.  A save whose writer reported but whose trainer never asked (abort between the
+    two) must not hand its results to the following save -- that would put the wrong storage offsets into ``.metadata``."""
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+
+    q = AsyncCallsQueue(persistent=False)
+    try:
+        abandoned = {"other": {"z": torch.arange(5)}}
+        ret = _async_save(abandoned, tmp_path / "abandoned", q)
+        import time
+
+        # the writer of the abandoned save runs to completion and reports ...
+
+        deadline = time.time() + 60
+        while not any(f.endswith(".distcp") for f in os.listdir(tmp_path / "abandoned")) and time.time() < deadline:
+            time.sleep(0.05)
+        time.sleep(0.5)
+        q.close(abort=True)  # ... but the trainer aborts before finalizing: nobody retrieves that report
+        del ret
+        q = AsyncCallsQueue(persistent=False)
+        state = _state()
+        _async_save(state, tmp_path / "next", q)
+        q.maybe_finalize_async_calls(blocking=True)
+        _loaded_equals(tmp_path / "next", _state())
+    finally:
+        q.close()

@@ -259,18 +259,21 @@ def test_abort_gives_host_slots_back(monkeypatch, built_library, shm_dir, dist_1
         ckpt = TorchAsyncCheckpoint(persistent_queue=True)
         q = AsyncCallsQueue(persistent=True)
         try:
-            for round_ in range(2):  # three saves per round: more than the pool has slots
-                ckpt.async_save(_state(round_), shm_dir / f"a{round_}.pt")
-                dev_state = {"m": {"w": FakeCudaTensor.wrap(torch.randn(100, 10))}}
-                writer = FileSystemWriterAsync(shm_dir / f"dcp{round_}", thread_count=1)
-                save_state_dict_async_plan(dev_state, writer, None, 0)
-                save_fn, preload_fn, save_args = writer.get_save_function_and_args()
-                q.schedule_async_request(AsyncRequest(save_fn, save_args, [], preload_fn=preload_fn))
-                abort_nvrx_checkpoint()
-                del writer  # the aborted DCP save never reaches retrieve_write_results
-                ckpt.async_save(_state(100 + round_), shm_dir / f"b{round_}.pt")  # works again right away
-                ckpt.finalize_async_save(blocking=True)
-                _same(torch.load(shm_dir / f"b{round_}.pt", weights_only=False), _state(100 + round_, wrap=False))
+            # two saves in flight (they hold two of the four slots of the pool), then the abort
+            ckpt.async_save(_state(0), shm_dir / "a0.pt")
+            dev_state = {"m": {"w": FakeCudaTensor.wrap(torch.randn(100, 10))}}
+            writer = FileSystemWriterAsync(shm_dir / "dcp0", thread_count=1)
+            save_state_dict_async_plan(dev_state, writer, None, 0)
+            save_fn, preload_fn, save_args = writer.get_save_function_and_args()
+            q.schedule_async_request(AsyncRequest(save_fn, save_args, [], preload_fn=preload_fn))
+            abort_nvrx_checkpoint()
+            del writer  # the aborted DCP save never reaches retrieve_write_results
+            for i in range(5):  # more saves than the pool has slots: they only fit if the aborted ones gave theirs back
+                ckpt.async_save(_state(100 + i), shm_dir / f"b{i}.pt")
+                if i % 2:
+                    ckpt.finalize_async_save(blocking=True)
+            ckpt.finalize_async_save(blocking=True)
+            _same(torch.load(shm_dir / "b4.pt", weights_only=False), _state(104, wrap=False))
             assert len(engine._slots) <= engine.max_host_slots and not any(s.busy for s in engine._slots)
         finally:
             ckpt.close()
