@@ -67,7 +67,8 @@ def _worker(rank, world, root, mode, zero_copy, kill):
                 q.schedule_async_request(req)
                 assert q.maybe_finalize_async_calls(blocking=True, no_dist=False)
                 assert engine.last_exchange == {"nccl": "nccl-allgather", "stream": "nccl-streamed"}[mode]
-                files = sorted(p.name for p in mgr.local_ckpt_dir.iterdir())
+                # (the previous iteration's files are removed by a background thread: look at this iteration's only)
+                files = sorted(p.name for p in mgr.local_ckpt_dir.iterdir() if p.name.startswith(f"iter_{it:07d}_"))
                 assert files == sorted(f"iter_{it:07d}_{m}_local.pt" for m in range(world)), files
                 for m in range(world):
                     path = mgr.local_ckpt_dir / f"iter_{it:07d}_{m}_local.pt"
