@@ -83,7 +83,7 @@ def _worker(rank, world, root, mode, zero_copy, kill):
             dist.barrier()
             if rank in kill:
                 for p in mgr.local_ckpt_dir.iterdir():
-                    p.unlink()
+                    p.unlink(missing_ok=True)  # the background cleanup of the previous iteration may get there first
             dist.barrier()
             mgr2 = LocalCheckpointManager(root, repl_strategy=strat)
             assert mgr2.find_latest() == 5
@@ -152,7 +152,7 @@ def _sharded_worker(rank, world, root, kill):
             dist.barrier()
             if rank in kill:
                 for p in mgr.local_ckpt_dir.iterdir():
-                    p.unlink()
+                    p.unlink(missing_ok=True)  # the background cleanup of the previous iteration may get there first
             dist.barrier()
             mgr2 = ShardedLocalCheckpointManager(root, clique=mgr.clique)
             assert mgr2.find_latest() == 2
