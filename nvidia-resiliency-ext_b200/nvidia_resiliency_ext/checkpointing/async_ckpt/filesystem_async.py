@@ -279,7 +279,10 @@ class FileSystemWriterAsync(FileSystemWriter):
     def __del__(self):
         # a save that was aborted (in-process restart) never reaches retrieve_write_results: give its host slot back and mark
         # whatever its writer may still report as nobody's
-        _live_saves.discard(getattr(self, "_save_id", None))
+        try:
+            _live_saves.discard(getattr(self, "_save_id", None))
+        except Exception:  # noqa: BLE001 - module globals are gone at interpreter shutdown
+            pass
         snap, self._snapshot = getattr(self, "_snapshot", None), None
         if snap is not None:
             try:
