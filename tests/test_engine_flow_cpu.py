@@ -299,3 +299,47 @@ def test_warmup_creates_the_resources_of_the_first_save(monkeypatch, built_libra
             assert ckpt.warmup({"x": torch.ones(3)}) == 0  # host state: nothing to prepare
         finally:
             ckpt.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_sequences_of_saves_deletes_restores(monkeypatch, built_library, shm_dir, tmp_path, dist_1rank, seed):
+    """Slot life cycle under a random workload: zero-copy and copying saves to /dev/shm and to another file system, files
+    deleted or kept, structures changing, trims in between.  Invariants: every file that exists loads back exactly, kept files
+    are never disturbed by later snapshots, the pool respects its bound, nothing stays busy."""
+    import random
+
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
+
+    rng = random.Random(seed)
+    monkeypatch.setenv("NVRX_B200_GPU_CRC", "1" if seed == 2 else "0")
+    with fake_device(monkeypatch) as (engine, lib):
+        ckpt = TorchAsyncCheckpoint(persistent_queue=False)
+        alive = {}  # path -> expected state
+        try:
+            for step in range(14):
+                monkeypatch.setenv("NVRX_B200_ZERO_COPY", rng.choice(["1", "1", "0"]))
+                base = shm_dir if rng.random() < 0.75 else tmp_path
+                path = base / f"s{step}.pt"
+                sd = _state(step)
+                if rng.random() < 0.3:  # a structure change: other sizes, one tensor more
+                    sd["model"]["extra"] = FakeCudaTensor.wrap(torch.randn(rng.randint(1, 5000)))
+                want = {"model": {k: plain(v).clone() for k, v in sd["model"].items()}, "opt": [plain(sd["opt"][0]).clone(), {"m": plain(sd["opt"][1]["m"]).clone()}],
+                        "blob": plain(sd["blob"]).clone(), "iteration": sd["iteration"]}
+                ckpt.async_save(sd, path)
+                for t in _flat(sd):
+                    if t.numel():
+                        plain(t).zero_()
+                ckpt.finalize_async_save(blocking=True)
+                alive[path] = want
+                for p, w in alive.items():  # nothing that is still on disk was disturbed
+                    _same(torch.load(p, weights_only=False), w)
+                if rng.random() < 0.6 and len(alive) > 1:
+                    victim = rng.choice(list(alive)[:-1])
+                    os.unlink(victim)
+                    del alive[victim]
+                if rng.random() < 0.15:
+                    engine.trim()
+                assert len(engine._slots) <= engine.max_host_slots and not any(s.busy for s in engine._slots)
+            assert len(engine._plans) <= 2 * 14 + 2
+        finally:
+            ckpt.close()
