@@ -301,8 +301,8 @@ def test_warmup_creates_the_resources_of_the_first_save(monkeypatch, built_libra
             ckpt.close()
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
-def test_random_sequences_of_saves_deletes_restores(monkeypatch, built_library, shm_dir, tmp_path, dist_1rank, seed):
+@pytest.mark.parametrize("seed,persistent", [(1, False), (2, False), (3, False), (4, True)])
+def test_random_sequences_of_saves_deletes_restores(monkeypatch, built_library, shm_dir, tmp_path, dist_1rank, seed, persistent):
     """Slot life cycle under a random workload: zero-copy and copying saves to /dev/shm and to another file system, files
     deleted or kept, structures changing, trims in between.  Invariants: every file that exists loads back exactly, kept files
     are never disturbed by later snapshots, the pool respects its bound, nothing stays busy."""
@@ -313,7 +313,7 @@ def test_random_sequences_of_saves_deletes_restores(monkeypatch, built_library, 
     rng = random.Random(seed)
     monkeypatch.setenv("NVRX_B200_GPU_CRC", "1" if seed == 2 else "0")
     with fake_device(monkeypatch) as (engine, lib):
-        ckpt = TorchAsyncCheckpoint(persistent_queue=False)
+        ckpt = TorchAsyncCheckpoint(persistent_queue=persistent)  # the persistent worker keeps slot mappings cached
         alive = {}  # path -> expected state
         try:
             for step in range(14):
