@@ -60,7 +60,11 @@ def _worker(rank, world, root, mode, zero_copy, kill):
             strat = CliqueReplicationStrategy.from_replication_params(1, world)
             mgr = LocalCheckpointManager(root, repl_strategy=strat)
             q = AsyncCallsQueue(persistent=False)
-            for it in (4, 5):  # twice: the second save reuses geometry, views and (in zero-copy mode) freed slots
+            import time
+
+            for it in (2, 3, 4, 5):  # steady state: later saves reuse geometry, views and (in zero-copy mode) freed slots
+                time.sleep(0.4)  # let the background cleanup of the iteration before last finish (saves are minutes apart)
+                dist.barrier()
                 sd = BasicTensorAwareStateDict(_rank_state(rank + 10 * it, FakeCudaTensor.wrap))
                 req = mgr.save(sd, it, is_async=True)
                 assert sd.is_hollow
@@ -80,6 +84,7 @@ def _worker(rank, world, root, mode, zero_copy, kill):
                         assert a.dtype == b.dtype and torch.equal(plain(a), b), (rank, m)
                     if zero_copy:
                         assert os.stat(path).st_nlink == 2, "replica file is expected to be a hard link to a slot"
+                assert len(engine._slots) <= engine.max_host_slots
             dist.barrier()
             if rank in kill:
                 for p in mgr.local_ckpt_dir.iterdir():
