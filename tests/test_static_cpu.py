@@ -12,3 +12,16 @@ def test_no_undefined_globals(capsys):
     rc = mod.main()
     out = capsys.readouterr().out
     assert rc == 0, out
+
+
+def test_the_product_never_imports_the_oracle_or_the_test_helpers():
+    """The oracle is the checker, not a fallback: nothing under the package (or in the C sources) may import or name it."""
+    import re
+
+    pkg = ROOT / "nvidia-resiliency-ext_b200"
+    offenders = []
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list((ROOT / "include").glob("*.h")):
+        text = path.read_text()
+        if re.search(r"^\s*(from|import)\s+(oracle|_fake_device|tests)\b", text, re.M) or "oracle/" in text and path.suffix in (".cu", ".cuh", ".h"):
+            offenders.append(str(path))
+    assert not offenders, offenders
