@@ -125,7 +125,7 @@ def _try_link(obj, target: str, records, protocol) -> bool:
     from . import ptzip
 
     slot, offsets, sizes = _single_slot(records)
-    if slot is None:
+    if slot is None or not hasattr(torch.serialization, "skip_data"):
         return False
     crcs = None
     info = getattr(slot, "crc_info", None)
@@ -167,7 +167,7 @@ def save(obj, f, *args, **kwargs) -> str:
         # opened on its name by the caller, exclusively in the managers' case; the container is written through the name.)
         slot, offsets, sizes = _single_slot(records)
         info = getattr(slot, "crc_info", None) if slot is not None else None
-        if info and protocol == torch.serialization.DEFAULT_PROTOCOL:
+        if info and protocol == torch.serialization.DEFAULT_PROTOCOL and hasattr(torch.serialization, "skip_data"):
             from . import ptzip
 
             ptzip.save(obj, named, locate=_locate_or_none, threads=WRITE_THREADS, crcs=_gpu_crcs(slot, info, offsets, sizes))
