@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """Benchmark of the checkpoint-snapshot hot path (BASELINE.json metric), one process per GPU.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's engine
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's own path (oracle port), host cores
+    python bench.py --gpus N --steps K --warmup W                    # this repo's engine, config C2
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own path (oracle port), same loop
+    python bench.py --config c3 ...                                  # C3: fp32->bf16 narrowing in the pack kernel
+    python bench.py --config c4 --gpus 8 ...                         # C4/C5: replicated local checkpoints (bench_c4.py)
 
-Workload (N=1 and every N: weak scaling, no data-path collective): BASELINE config C2 -- per rank a 1/8 row
-shard of Llama-3-8B in 4 fp32 copies (param, main_param, exp_avg, exp_avg_sq) = 1164 tensors, 16,060,522,496 B,
-plus 291 scalar fp32 `step` tensors, synthetic values.  ``--narrow`` switches to C3.
+Workload (every N: weak scaling, no data-path collective for C2/C3): per rank a 1/8 row shard of Llama-3-8B in 4 fp32
+copies (param, main_param, exp_avg, exp_avg_sq) = 1164 tensors, 16,060,522,496 B, plus 291 scalar fp32 `step` tensors,
+synthetic values.
 
-One "step" = one snapshot of the whole state dict.
-  value      device snapshot rate: S bytes / pack-kernel time (state resident in HBM; inputs >> L2 so no flush),
-             CUDA events on the launching stream, K back-to-back launches, max over ranks, summed over ranks.
-  roofline   algorithmic HBM bytes of one pack launch (2*S, or 1.5*S_in when narrowing) / that time, against the
-             measured copy peak in MEASURED_PEAKS.json.
-  e2e        same metric through the public API (TorchAsyncCheckpoint.async_save on the GPU state dict) until the
-             snapshot bytes are in host memory: includes the D2H of the whole snapshot every step.
-  stall_ms   how long the training stream is held up by async_save (call + pack kernel); persist_s: until
-             finalize_async_save(blocking=True) returned (file on /dev/shm loadable by torch.load).
-  cpu_baseline / --impl reference: the reference's save path (per-tensor pinned D2H + cuda sync + fork + torch.save),
-             oracle port, timed on this box's host cores.
+BOTH arms run the SAME loop (``api_loop``) over the same state dict on EVERY rank; only the object behind it differs:
+the product's ``TorchAsyncCheckpoint`` or the port of the reference's ``TorchAsyncCheckpoint`` flow
+(``oracle/reference_port.py``).  One step = one checkpoint of the whole state dict through ``async_save(state_dict, path)``.
+
+  value       state bytes of all ranks / STALL: the wall time ``async_save`` keeps the training stream blocked (from the
+              call until an event recorded on the training stream right after it has completed).  The state is resident
+              in HBM when the timed region starts; this is the "snapshot GB/s" a training loop sees.  ms_per_step = that
+              stall (mean of the K steps, max over ranks).
+  e2e         same metric until the snapshot bytes are SAFE IN HOST MEMORY (the D2H of the whole snapshot is inside the
+              timed region): PCIe-bound in both arms.
+  stall_beside_training_ms   the same stall measured inside a running GEMM loop: extra wall time of a window of
+              training steps when one checkpoint is taken in the middle of it.
+  persist_s   until ``finalize_async_save(blocking=True)`` returned (file loadable by ``torch.load``);
+  restore_s   ``LocalCheckpointManager.find_latest() + load()`` of the same state from its local checkpoint file.
+  roofline    (engine arm) the pack kernel alone: algorithmic HBM bytes of one launch (2*S; 1.5*S_in when narrowing) /
+              its duration, K back-to-back launches timed with CUDA events on the launching stream, against the measured
+              copy peak in MEASURED_PEAKS.json.  This kernel rate is NOT the headline; it explains the stall.
+  cpu_baseline (engine arm, N=1) a short run of the reference loop on the same box, for the record.
 """
 import argparse
 import json
@@ -39,6 +48,12 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "checkpoint_snapshot_GBps"
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+WORKLOADS = {
+    "c2": "C2: 16.06 GB Llama-3-8B-shaped param+Adam state_dict per rank (1164 fp32 tensors + 291 scalar steps), "
+          "snapshot through TorchAsyncCheckpoint.async_save -> pinned host -> file on /dev/shm",
+    "c3": "C3: 16.06 GB Llama-3-8B-shaped param+Adam state_dict per rank (1164 fp32 tensors + 291 scalar steps), "
+          "fp32->bf16 narrow in the pack kernel, snapshot through TorchAsyncCheckpoint.async_save -> pinned host -> file on /dev/shm",
+}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -75,6 +90,11 @@ def llama3_8b_shard_state(device, seed=1234, scale=1.0):
         opt[i] = {"main_param": m, "exp_avg": ea, "exp_avg_sq": es, "step": torch.tensor(float(1000 + i), device=device)}
         total += 4 * p.numel() * 4 + 4
     return {"model": model, "optimizer": {"state": opt}}, total
+
+
+def fresh_containers(sd):
+    """New nested containers around the same tensors (LocalCheckpointManager.save rewrites the container it is given)."""
+    return {"model": dict(sd["model"]), "optimizer": {"state": {k: dict(v) for k, v in sd["optimizer"]["state"].items()}}}
 
 
 def flatten(sd):
@@ -157,15 +177,18 @@ def hbm_peak():
 
 
 def ncu_traffic(label_prefix):
-    """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` capture."""
-    p = ROOT / "profiles" / "r01_ncu_walk_summary.json"
-    try:
-        for k in json.load(open(p))["kernels"]:
-            if k["label"].startswith(label_prefix):
-                return float(k["traffic_bytes"])
-    except Exception:  # noqa: BLE001
-        pass
-    return None
+    """dram read+write bytes per launch of the dominant kernel from the newest committed `ncu --set full` summary, with the
+    commit that summary was captured at (the number is a cross-check, not a live measurement)."""
+    for name in ("r02_ncu_walk_summary.json", "r01_ncu_walk_summary.json"):
+        p = ROOT / "profiles" / name
+        try:
+            doc = json.load(open(p))
+            for k in doc["kernels"]:
+                if k["label"].startswith(label_prefix):
+                    return float(k["traffic_bytes"]), f"profiles/{name} (ncu --set full, same state, one launch; captured at commit {doc.get('commit', 'round 1')})"
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
 
 
 def init_dist(n_gpus):
@@ -186,38 +209,268 @@ def max_over_ranks(x: float) -> float:
     return t.item()
 
 
+def min_over_ranks(x: float) -> float:
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return t.item()
+
+
+def mean(xs):
+    return sum(xs) / len(xs)
+
+
 def median(xs):
     s = sorted(xs)
     return s[len(s) // 2]
 
 
-def shm_dir(rank):
+def shm_dir(rank, tag="bench"):
     base = Path("/dev/shm") if os.access("/dev/shm", os.W_OK) else Path("/tmp")
-    d = base / f"nvrx_b200_bench_{os.getpid()}_{rank}"
+    d = base / f"nvrx_b200_{tag}_{os.getpid()}_{rank}"
     d.mkdir(parents=True, exist_ok=True)
     return d
 
 
+def bits_equal(a, b):
+    return a.dtype == b.dtype and a.shape == b.shape and (
+        a.numel() == 0 or torch.equal(a.contiguous().view(-1).view(torch.uint8), b.contiguous().view(-1).view(torch.uint8)))
+
+
 # ----------------------------------------------------------------------------------------------------
-# arms
+# the two arms behind one interface
 # ----------------------------------------------------------------------------------------------------
-def run_engine(args, rank, world, local):
-    from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
+class EngineArm:
+    """The product: nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt.TorchAsyncCheckpoint (public API)."""
+
+    name = "engine"
+    writes_every_step = True
+
+    def __init__(self, narrow):
+        from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
+
+        self.ckpt = TorchAsyncCheckpoint(persistent_queue=True, narrow_fp32_to_bf16=narrow)
+
+    def save(self, sd, path, write=True):
+        self.ckpt.async_save(sd, path)
+
+    def host_safe(self):
+        for snap in list(self.ckpt._pending.values()):
+            snap.wait()  # CPU wait on the drain's event: bytes are in pinned host memory
+
+    def finalize(self):
+        self.ckpt.finalize_async_save(blocking=True, no_dist=True)
+
+    def close(self):
+        self.ckpt.close()
+
+
+class ReferenceArm:
+    """The reference's flow (oracle/reference_port.py, port of async_ckpt/torch_ckpt.py:43-53 + core.py:318-355)."""
+
+    name = "reference"
+    writes_every_step = False
+
+    def __init__(self, narrow):
+        from oracle.reference_port import ReferenceAsyncCheckpoint
+
+        self.ckpt = ReferenceAsyncCheckpoint()  # the reference has no narrowing: C3's reference arm is C2's
+
+    def save(self, sd, path, write=True):
+        self.ckpt.async_save(sd, path, write=write)
+
+    def host_safe(self):
+        pass  # async_save returned after torch.cuda.synchronize(): the host copies are complete
+
+    def finalize(self):
+        self.ckpt.finalize(blocking=True)
+
+    def close(self):
+        self.ckpt.finalize(blocking=True)
+
+
+def api_loop(arm, sd, path, steps, warmup, persist_steps):
+    """K checkpoints through ``arm``; per step: stall, time to host-safe, time to persisted (only when the step wrote)."""
+    ev = torch.cuda.Event()
+    stall, safe, persist = [], [], []
+    for it in range(warmup + steps):
+        write = arm.writes_every_step or it >= warmup + steps - persist_steps
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        arm.save(sd, path, write)
+        ev.record()
+        ev.synchronize()  # the training stream is free again here
+        t1 = time.perf_counter()
+        arm.host_safe()
+        t2 = time.perf_counter()
+        arm.finalize()
+        t3 = time.perf_counter()
+        if it >= warmup:
+            stall.append(t1 - t0)
+            safe.append(t2 - t0)
+            if write:
+                persist.append(t3 - t0)
+    return stall, safe, persist
+
+
+class TrainingLoop:
+    """Dummy training step: a fixed number of bf16 8192^3 GEMMs on the current stream."""
+
+    def __init__(self, dev, step_ms=30.0):
+        self.a = torch.randn(8192, 8192, dtype=torch.bfloat16, device=dev)
+        self.b = torch.randn(8192, 8192, dtype=torch.bfloat16, device=dev)
+        self.c = torch.empty(8192, 8192, dtype=torch.bfloat16, device=dev)
+        self.gemms = 8
+        ms = self._time(3)
+        self.gemms = max(4, int(round(self.gemms * step_ms / max(ms, 1e-3))))
+        self.step_ms = self._time(5)
+
+    def step(self, n=1):
+        for _ in range(n * self.gemms):
+            torch.mm(self.a, self.b, out=self.c)
+
+    def _time(self, n):
+        self.step(2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.step(n)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / n
+
+
+def stall_beside_training(arm, sd, path, loop, reps, before=10, after=30):
+    """Extra wall time of a window of ``before + after`` training steps when ONE checkpoint is taken after ``before`` of
+    them (device idle at both ends of the window).  The window is longer than the background drain, so the number holds
+    everything the checkpoint costs the training loop: the call, the pack kernel(s) in stream order, and whatever the
+    side-stream D2H takes away from the GEMMs."""
+    base, with_ckpt = [], []
+    for r in range(reps + 1):
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loop.step(before + after)
+        torch.cuda.synchronize()
+        t_base = time.perf_counter() - t0
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loop.step(before)
+        arm.save(sd, path, arm.writes_every_step)
+        loop.step(after)
+        torch.cuda.synchronize()
+        t_with = time.perf_counter() - t0
+        arm.host_safe()
+        arm.finalize()
+        if r > 0:  # first repetition warms up
+            base.append(t_base)
+            with_ckpt.append(t_with)
+    return (median(with_ckpt) - median(base)) * 1e3, median(base) * 1e3
+
+
+def d2h_ceiling(dev, world, gb=16.0):
+    """What the box gives N concurrent plain device->pinned-host copies (cudaMemcpyAsync into cudaHostAlloc memory, all
+    ranks at once): the PCIe / host-memory ceiling the e2e number can be judged against."""
+    n = 1 << 30
+    src = torch.empty(n, dtype=torch.uint8, device=dev)
+    dst = torch.empty(n, dtype=torch.uint8).pin_memory()
+    reps = max(1, int(gb))
+    for _ in range(2):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dist.barrier()
+    rate = reps * n / dt / 1e9
+    return {"per_gpu_min_GBps": round(min_over_ranks(rate), 2), "per_gpu_max_GBps": round(max_over_ranks(rate), 2),
+            "what": f"{world} concurrent torch pinned-memory D2H copies, {reps} x 1 GiB each (cudaHostAlloc buffer, plain cudaMemcpyAsync)"}
+
+
+def local_manager_leg(arm_name, sd, tensors, total, rank, narrow):
+    """C5 on every rank independently (no replication): local checkpoint save through ``LocalCheckpointManager`` and
+    restore with ``find_latest() + load()``; the reference arm runs the port of the same two flows."""
+    root = shm_dir(rank, "local")
+    ev = torch.cuda.Event()
+    out = {}
+    try:
+        if arm_name == "engine":
+            from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+            from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+            from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+            mgr = LocalCheckpointManager(root, session_id=f"r{rank}")
+            q = AsyncCallsQueue(persistent=False)
+            tasd = BasicTensorAwareStateDict(fresh_containers(sd))
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            req = mgr.save(tasd, 1, is_async=True)
+            ev.record()
+            ev.synchronize()
+            t1 = time.perf_counter()
+            q.schedule_async_request(req)
+            q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+            t2 = time.perf_counter()
+            q.close()
+            del tasd, req
+            mgr2 = LocalCheckpointManager(root, session_id=f"r{rank}")
+            torch.cuda.synchronize()
+            dist.barrier()
+            t3 = time.perf_counter()
+            latest = mgr2.find_latest()
+            loaded, cid = mgr2.load()
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            got = list(loaded.tensors)
+            ok = latest == 1 and cid[0] == 1
+        else:
+            from oracle.reference_port import reference_local_load, reference_local_save
+
+            path = root / "iter_0000001_0_local.pt"
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            res = reference_local_save(fresh_containers(sd), path)
+            t1, t2 = t0 + res["stall"], t0 + res["total"]
+            torch.cuda.synchronize()
+            dist.barrier()
+            t3 = time.perf_counter()
+            loaded = reference_local_load(path)
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            got = flatten(loaded.state_dict)
+            ok = True
+        ok = ok and len(got) == len(tensors)
+        for a, b in list(zip(got, tensors))[:: max(1, len(tensors) // 48)]:
+            ok = ok and a.is_cuda and bits_equal(a, b)
+        del loaded, got
+        out = {
+            "local_save_stall_ms": round(max_over_ranks(t1 - t0) * 1e3, 2),
+            "local_save_persist_s": round(max_over_ranks(t2 - t0), 3),
+            "restore_s": round(max_over_ranks(t4 - t3), 3),
+            "restore_verify": "bit-exact" if ok else "MISMATCH",
+        }
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return out
+
+
+def kernel_leg(args, tensors, local):
+    """The pack kernel alone: K back-to-back launches, CUDA events on the launching stream, max over ranks."""
     from nvidia_resiliency_ext.checkpointing.b200.engine import Event, SnapshotEngine
 
-    dev = torch.device("cuda", local)
-    sd, total = llama3_8b_shard_state(dev, seed=1234 + rank, scale=args.scale)
-    tensors = flatten(sd)
-    engine = SnapshotEngine.get(local, host_slots=2)  # slots are created lazily; sequential steps use one
+    engine = SnapshotEngine.get(local, host_slots=2)
     stream = torch.cuda.current_stream().cuda_stream
-
-    # ---- kernel-only: K back-to-back pack launches (value, roofline) -------------------------------
     mask = SnapshotEngine._narrow_mask(tensors, args.narrow)
     plan = engine._plan_for(tensors, mask)
     staging = engine._ensure_staging(plan.staging_bytes)
-    clocks = ClockSampler(local)
-    clocks.__enter__()  # sampled from here until the end of the end-to-end loop (both timed regions)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         plan.pack(staging.ptr, stream)
     e0, e1 = Event(local, True), Event(local, True)
     torch.cuda.synchronize()
@@ -230,264 +483,202 @@ def run_engine(args, rank, world, local):
     kernel_ms = max_over_ranks(e0.elapsed_ms(e1) / args.steps)
     torch.cuda.synchronize()
     dist.barrier()
-    launches = args.steps
+    return engine, plan, kernel_ms
 
-    # ---- end to end through the public API -----------------------------------------------------------
-    # Host-memory budget: the box's cgroup (200 GiB on the 1-GPU boxes of this pool) also counts tmpfs / POSIX-shm
-    # pages.  One rank needs a 16 GB pinned slot; persisting adds a 16 GB file per rank.  With several ranks on a box
-    # the files would not fit (8 x 32 GB), so N>1 measures the snapshot through utils.preload_tensors (state -> pinned
-    # host, no file) and only N=1 runs the full TorchAsyncCheckpoint.async_save -> file -> restore cycle.
-    persist_files = world == 1 or args.persist
+
+def run_arm(args, rank, world, local):
+    dev = torch.device("cuda", local)
+    sd, total = llama3_8b_shard_state(dev, seed=1234 + rank, scale=args.scale)
+    tensors = flatten(sd)
+    engine_arm = args.impl == "engine"
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    launches = 0
+    engine = plan = None
+    kernel_ms = None
+    if engine_arm:
+        engine, plan, kernel_ms = kernel_leg(args, tensors, local)
+        launches += args.steps
+        launches_before = engine.launches
+
+    arm = (EngineArm if engine_arm else ReferenceArm)(args.narrow)
     out_dir = shm_dir(rank)
-    engine_launches_before = None
-    ckpt = TorchAsyncCheckpoint(persistent_queue=True, narrow_fp32_to_bf16=args.narrow) if persist_files else None
-    stall, host_safe, persist = [], [], []
-    done_ev = torch.cuda.Event()
     path = out_dir / "ckpt.pt"  # one file per rank, overwritten every step
-    from nvidia_resiliency_ext.checkpointing.utils import preload_tensors
-
-    for it in range(args.e2e_warmup + args.e2e_steps):
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        if persist_files:
-            ckpt.async_save(sd, path)
-            done_ev.record()
-            done_ev.synchronize()  # the training stream is free again here
-            t1 = time.perf_counter()
-            snap = next(iter(ckpt._pending.values()))
-            snap.wait()  # bytes are in host memory
-            t2 = time.perf_counter()
-            ckpt.finalize_async_save(blocking=True, no_dist=True)
-            t3 = time.perf_counter()
-        else:
-            _, snap = preload_tensors(sd, non_blocking=True, narrow=args.narrow, return_snapshot=True)
-            done_ev.record()
-            done_ev.synchronize()
-            t1 = time.perf_counter()
-            snap.wait()
-            t2 = t3 = time.perf_counter()
-            snap.release()
-        if it == args.e2e_warmup - 1 or (args.e2e_warmup == 0 and it == 0 and engine_launches_before is None):
-            engine_launches_before = engine.launches if args.e2e_warmup else 0
-        if it >= args.e2e_warmup:
-            stall.append(t1 - t0)
-            host_safe.append(t2 - t0)
-            persist.append(t3 - t0)
+    stall, safe, persist = api_loop(arm, sd, path, args.steps, args.warmup, args.persist_steps)
     clocks.__exit__(None, None, None)
-    launches += engine.launches - (engine_launches_before or 0)  # pack sub-launches of the pipelined snapshots
-    e2e_s = max_over_ranks(median(host_safe))
-    stall_ms = max_over_ranks(median(stall)) * 1e3
-    persist_s = max_over_ranks(median(persist))
-    linked = bool(persist_files and path.exists() and os.stat(path).st_nlink > 1)  # the file IS the pinned slot (opt-in mode)
+    stall_s = max_over_ranks(mean(stall))  # the K timed steps, mean -> ms_per_step
+    safe_s = max_over_ranks(mean(safe))
+    persist_s = max_over_ranks(median(persist)) if persist else None
+    linked = bool(path.exists() and os.stat(path).st_nlink > 1)  # the file IS the pinned slot (zero-copy publish)
+
     # spot-check the last file against the live state (bit-exact unless narrowed)
     check = "skipped"
-    if rank == 0 and not args.no_verify and persist_files:
-        loaded = torch.load(path, weights_only=False)
+    if rank == 0 and not args.no_verify and path.exists():
+        loaded = torch.load(path, weights_only=False, mmap=True)
         lt = flatten(loaded)
         ok = len(lt) == len(tensors)
         for a, b in list(zip(lt, tensors))[:: max(1, len(tensors) // 64)]:
-            want = b.to(torch.bfloat16).cpu() if (args.narrow and b.dtype == torch.float32 and b.numel() > 0) else b.cpu()
-            ok &= a.dtype == want.dtype and a.shape == want.shape and (
-                a.numel() == 0 or torch.equal(a.contiguous().view(-1).view(torch.uint8), want.contiguous().view(-1).view(torch.uint8)))
+            narrowed = engine_arm and args.narrow and b.dtype == torch.float32 and b.numel() > 0
+            ok &= bits_equal(a, b.to(torch.bfloat16).cpu() if narrowed else b.cpu())
         check = "bit-exact" if ok else "MISMATCH"
         del loaded, lt
-    # restore (C5 on one GPU): file -> mmap -> parallel gather into the pinned slot -> ONE H2D -> ONE scatter kernel
-    restore_s = None
-    if not args.no_restore and persist_files:
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        loaded = torch.load(path, weights_only=False, mmap=True)
-        lt = flatten(loaded)
-        widen = [torch.float32 if (args.narrow and t.dtype == torch.bfloat16) else None for t in lt]
-        resident = None
-        if os.environ.get("NVRX_B200_ZERO_COPY") == "1":  # opt-in: the file is a hard link to a slot that is still pinned
-            resident = engine.resident_source(path, lt)
-        file_source = None
-        if resident is None and os.environ.get("NVRX_B200_RESTORE_PREAD") == "1":  # opt-in A/B: pread instead of mmap gather
-            from nvidia_resiliency_ext.checkpointing.b200.ptzip import tensor_offsets_in_file
 
-            offs = tensor_offsets_in_file(path, lt)
-            file_source = (str(path), offs) if offs is not None else None
-        back = engine.restore(lt, widen_to=widen if args.narrow else None, resident=resident, file_source=file_source)
-        torch.cuda.synchronize()
-        restore_s = max_over_ranks(time.perf_counter() - t0)
-        launches += 1
-        if not args.narrow:
-            for a, b in list(zip(back, tensors))[:: max(1, len(tensors) // 32)]:
-                if not torch.equal(a.view(-1).view(torch.uint8), b.view(-1).view(torch.uint8)):
-                    check = "MISMATCH(restore)"
-        del loaded, lt, back
-    if ckpt is not None:
-        ckpt.close()
+    load_ms = base_ms = None
+    if not args.no_training_loop:
+        loop = TrainingLoop(dev)
+        load_ms, base_ms = stall_beside_training(arm, sd, path, loop, args.load_reps)
+        load_ms, base_ms = max_over_ranks(load_ms), max_over_ranks(base_ms)
+        del loop
+    arm.close()
     shutil.rmtree(out_dir, ignore_errors=True)
+    if engine_arm:
+        engine.trim()  # give the async slots back before the local-manager leg pins its own
+    local_leg = {} if args.no_restore else local_manager_leg(args.impl, sd, tensors, total, rank, args.narrow)
+    ceiling = None if args.no_ceiling else d2h_ceiling(dev, world)
+    if engine_arm:
+        launches += engine.launches - launches_before
 
-    packed_bytes = plan.staging_bytes
-    algo = plan.algorithmic_bytes
-    peak, peak_src = hbm_peak()
-    achieved = algo / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC,
-        "value": round(world * total / (kernel_ms * 1e-3) / 1e9, 1),
+        "value": round(world * total / stall_s / 1e9, 1),
         "unit": "GB/s",
         "n_gpus": world,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": round(kernel_ms, 4),
+        "ms_per_step": round(stall_s * 1e3, 4),
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "bf16-narrowed bytes" if args.narrow else "u8",
+        "dtype": "u8" if not (args.narrow and engine_arm) else "f32->bf16 (rne) + u8",
         "data": "synthetic",
+        "impl": args.impl,
+        "value_definition": "state bytes of all ranks / training-stream stall of async_save (state resident in HBM; until the "
+                            "training stream is free again), public API, same loop in both arms",
         "config": {
-            "workload": ("C3" if args.narrow else "C2") + ": 16.06 GB Llama-3-8B-shaped param+Adam state_dict per rank "
-                        "(1164 fp32 tensors + 291 scalar steps), pack + D2H drain",
+            "workload": WORKLOADS[args.config],
             "state_bytes_per_rank": total,
-            "packed_bytes_per_rank": packed_bytes,
             "tensors": len(tensors),
             "l2": "inputs (16 GB) >> L2 (126 MB); no flush needed",
-            "walker": os.environ.get("NVRX_B200_VARIANT", "auto"),
             "scale": args.scale,
+            "path": ("nvidia_resiliency_ext...TorchAsyncCheckpoint.async_save (pack kernel on the training stream, side-stream drain, "
+                     "writer process follows the drain)" if engine_arm else
+                     "reference flow (oracle/reference_port.py): per-tensor pinned D2H + torch.cuda.synchronize() + fork + torch.save"
+                     + ("; the reference has no narrowing, it saves fp32" if args.narrow else "")),
         },
         "e2e": {
-            "value": round(world * total / e2e_s / 1e9, 2),
+            "value": round(world * total / safe_s / 1e9, 2),
             "unit": "GB/s",
-            "h2d_bytes_per_step": int(len(tensors) * 32),
-            "d2h_bytes_per_step": int(packed_bytes),
-            "definition": ("state bytes / wall time from TorchAsyncCheckpoint.async_save() until the snapshot is in pinned host memory"
-                           if persist_files else
-                           "state bytes / wall time from checkpointing.utils.preload_tensors() until the snapshot is in pinned host memory "
-                           "(no file at N>1: host-memory budget of the box)"),
-            "steps": args.e2e_steps,
+            "h2d_bytes_per_step": int(len(tensors) * 32) if engine_arm else 0,
+            "d2h_bytes_per_step": int(plan.staging_bytes) if engine_arm else int(total),
+            "definition": "state bytes of all ranks / wall time from async_save() until the snapshot is safe in host memory",
+            "per_gpu_GBps": round(total / safe_s / 1e9, 2),
+            "d2h_ceiling": ceiling,
         },
-        "stall_ms": round(stall_ms, 3),
-        "persist_s": round(persist_s, 3) if persist_files else None,
-        "persist_GBps": round(world * total / persist_s / 1e9, 2) if persist_files else None,
-        "persist_mode": (("zero-copy link" if linked else "parallel copy") if persist_files else None),
-        "restore_s": None if restore_s is None else round(restore_s, 3),
-        "restore_GBps": None if restore_s is None else round(world * total / restore_s / 1e9, 2),
+        "stall_ms": round(stall_s * 1e3, 3),
+        "stall_beside_training_ms": None if load_ms is None else round(load_ms, 3),
+        "training_window_ms": None if base_ms is None else round(base_ms, 1),
+        "persist_s": None if persist_s is None else round(persist_s, 3),
+        "persist_GBps": None if persist_s is None else round(world * total / persist_s / 1e9, 2),
+        "persist_mode": ("zero-copy link" if linked else "parallel copy") if engine_arm else "torch.save in the forked child (1 core per rank)",
+        "persist_steps": len(persist),
+        **local_leg,
+        "restore_GBps": round(world * total / local_leg["restore_s"] / 1e9, 2) if local_leg.get("restore_s") else None,
         "gpu_launches": launches,
-        "roofline": {
-            "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": args.traffic_bytes or ncu_traffic("pack LDG narrow" if args.narrow else "pack TMA"),
-            "traffic_source": "profiles/r01_ncu_walk_summary.json (ncu --set full, same state, one launch)", "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
-            "kernel": "nvrx::walk_tma<pack>" if not args.narrow else "nvrx::walk_ldg<pack> (narrow)",
-        },
         "clocks": clocks.summary(),
         "verify": check,
+        "host_cores_on_box": os.cpu_count(),
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(sd, total, out_dir.parent, sample_gb=args.baseline_sample_gb)
+    if engine_arm:
+        peak, peak_src = hbm_peak()
+        algo = plan.algorithmic_bytes
+        achieved = algo / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = (args.traffic_bytes, "command line") if args.traffic_bytes else ncu_traffic("pack LDG narrow" if args.narrow else "pack TMA")
+        line["config"]["packed_bytes_per_rank"] = plan.staging_bytes
+        line["config"]["walker"] = os.environ.get("NVRX_B200_VARIANT", "auto")
+        line["roofline"] = {
+            "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+            "kernel": "nvrx::walk_tma<pack>" if not args.narrow else "nvrx::walk_ldg<pack> (narrow)",
+            "kernel_ms": round(kernel_ms, 4), "device_snapshot_GBps": round(world * total / (kernel_ms * 1e-3) / 1e9, 1),
+            "timing": f"{args.steps} back-to-back launches of the whole-state pack, CUDA events on the launching stream, max over ranks",
+        }
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sd, total, args.baseline_sample_gb)
+    else:
+        line["cpu_baseline"] = {
+            "value": line["value"], "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"every step, every rank: full-state per-tensor pinned D2H + torch.cuda.synchronize() (the stall); the forked "
+                      f"torch.save child (1 core per rank of {os.cpu_count()}) ran on the last {len(persist)} step(s) on the full state",
+        }
+        line["e2e"]["h2d_bytes_per_step"] = 0
+        line["e2e"]["d2h_bytes_per_step"] = 0
+        line["gpu_launches"] = 0
     return line
 
 
-def cpu_baseline(sd, total, base_dir, sample_gb):
-    """The reference save path (oracle port) on this box: D2H of the FULL state (stall), persistence on a bounded
+def cpu_baseline(sd, total, sample_gb):
+    """A short run of the reference loop (same ``api_loop``) on this box: stall on the full state, persistence on a bounded
     sample of the tensors."""
     from oracle import snapshot_oracle as orc
 
+    arm = ReferenceArm(False)
+    out = shm_dir(0, "cpubase")
+    stall, safe, _ = api_loop(arm, sd, out / "x.pt", 2, 1, 0)
+    arm.close()
     tensors = flatten(sd)
-    # warm the pinned-memory cache like a second checkpoint would see it
-    orc.reference_preload(sd)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    pre = orc.reference_preload(sd)
-    torch.cuda.synchronize()
-    d2h = time.perf_counter() - t0
-    del pre
     sample, acc = {}, 0
     for i, t in enumerate(tensors):
         if acc + t.numel() * 4 > sample_gb * 1e9:
             continue
         sample[f"t{i}"] = t
         acc += t.numel() * 4
-    path = Path(base_dir) / f"nvrx_ref_sample_{os.getpid()}.pt"
-    res = orc.reference_fork_save(sample, path)
-    path.unlink(missing_ok=True)
+    res = orc.reference_fork_save(sample, out / "sample.pt")
+    shutil.rmtree(out, ignore_errors=True)
     persist_rate = acc / (res["total"] - res["d2h"]) / 1e9
+    d2h = mean(stall)
     return {
         "value": round(total / d2h / 1e9, 2), "unit": "GB/s", "cores": 1, "kind": "port",
-        "sample": f"full-state per-tensor pinned D2H + cuda sync (stall {d2h*1e3:.0f} ms); fork + torch.save timed on "
-                  f"{acc/1e9:.2f} GB of the tensors ({persist_rate:.2f} GB/s, 1 core)",
+        "sample": f"reference loop, 2 steps on the full state: per-tensor pinned D2H + cuda sync (stall {d2h*1e3:.0f} ms); fork + "
+                  f"torch.save timed on {acc/1e9:.2f} GB of the tensors ({persist_rate:.2f} GB/s, 1 core)",
         "stall_ms": round(d2h * 1e3, 1), "persist_GBps_1core": round(persist_rate, 2), "host_cores_on_box": os.cpu_count(),
-    }
-
-
-def run_reference(args, rank, world, local):
-    """The reference's own path (oracle port of utils.preload_tensors + torch_ckpt.async_save + fork/torch.save)."""
-    from oracle import snapshot_oracle as orc
-
-    if rank != 0:
-        return None
-    dev = torch.device("cuda", local)
-    sd, total = llama3_8b_shard_state(dev, seed=1234, scale=args.scale)
-    tensors = flatten(sd)
-    out_dir = shm_dir(rank)
-    times = []
-    for it in range(args.warmup + args.steps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        pre = orc.reference_preload(sd)  # per-tensor .to("cpu", non_blocking=True)  (utils.py:85-99)
-        torch.cuda.synchronize()         # torch_ckpt.py:50
-        dt = time.perf_counter() - t0
-        del pre
-        if it >= args.warmup:
-            times.append(dt)
-    d2h = median(times)
-    sample, acc = {}, 0
-    for i, t in enumerate(tensors):
-        if acc + t.numel() * 4 > args.baseline_sample_gb * 1e9:
-            continue
-        sample[f"t{i}"] = t
-        acc += t.numel() * 4
-    res = orc.reference_fork_save(sample, out_dir / "ref.pt")
-    shutil.rmtree(out_dir, ignore_errors=True)
-    persist_rate = acc / (res["total"] - res["d2h"]) / 1e9
-    value = round(total / d2h / 1e9, 2)
-    return {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(d2h * 1e3, 2), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C2: 16.06 GB Llama-3-8B-shaped param+Adam state_dict per rank (1164 fp32 tensors + 291 scalar steps), "
-                               "reference path: per-tensor pinned D2H + torch.cuda.synchronize()", "state_bytes_per_rank": total,
-                   "tensors": len(tensors), "scale": args.scale},
-        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "stall_ms": round(d2h * 1e3, 2),
-        "persist_GBps": round(persist_rate, 2),
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port",
-                         "sample": f"every step: full-state preload_tensors + cuda sync; once: fork + torch.save of {acc/1e9:.2f} GB "
-                                   f"({persist_rate:.2f} GB/s on 1 of {os.cpu_count()} host cores)"},
-        "gpu_launches": 0,
     }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--narrow", action="store_true", help="C3: fp32->bf16 in the pack kernel")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-warmup", type=int, default=1)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--narrow", action="store_true", help="alias of --config c3: fp32->bf16 in the pack kernel")
+    ap.add_argument("--persist-steps", type=int, default=1, help="reference arm: how many of the steps run the forked torch.save")
+    ap.add_argument("--load-reps", type=int, default=3, help="repetitions of the stall-beside-training measurement")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the state (debug only; numbers at != 1.0 are not C2)")
     ap.add_argument("--baseline-sample-gb", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-restore", action="store_true")
-    ap.add_argument("--persist", action="store_true", help="write checkpoint files at N>1 too (needs ~32 GB of host memory per rank)")
+    ap.add_argument("--no-training-loop", action="store_true")
+    ap.add_argument("--no-ceiling", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram read+write bytes per launch from the ncu capture")
-    args = ap.parse_args()
+    args, rest = ap.parse_known_args()
+    if args.narrow:
+        args.config = "c3"
+    args.narrow = args.config == "c3"
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else max(args.warmup, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the snapshot path has no CPU fallback)")
     rank, world, local = init_dist(args.gpus)
-    line = run_reference(args, rank, world, local) if args.impl == "reference" else run_engine(args, rank, world, local)
+    if args.config == "c4":
+        import bench_c4
+
+        line = bench_c4.run(args, rest, rank, world, local)
+    else:
+        line = run_arm(args, rank, world, local)
     if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
-    if args.impl == "engine":
-        dist.barrier()
+    dist.barrier()
     dist.destroy_process_group()
 
 

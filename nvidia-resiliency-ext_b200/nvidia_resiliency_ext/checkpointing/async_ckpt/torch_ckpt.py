@@ -42,16 +42,23 @@ class TorchAsyncCheckpoint(object):
             self._async_calls_queue.schedule_async_request(request)
             return
         devices = {t.device.index for t in tensors if t.is_cuda}
-        if len(devices) != 1 or not all(t.is_cuda for t in tensors):
-            raise ValueError("async_save: all tensors of the state dict must live on one CUDA device (or all on the host)")
+        if len(devices) != 1:
+            raise ValueError("async_save: the CUDA tensors of the state dict must live on one device")
         from ..b200.engine import SnapshotEngine
 
-        # GPU work first (pack sub-launches + drain are enqueued here), Python bookkeeping while it runs
-        snap = SnapshotEngine.get(devices.pop()).snapshot(tensors, narrow=self._narrow)
-        counter = iter(range(len(tensors)))
-        skeleton = dict_list_map_outplace(
-            lambda v: SnapshotRef(next(counter)) if isinstance(v, torch.Tensor) else v, state_dict
-        )
+        # GPU work first (pack sub-launches + drain are enqueued here), Python bookkeeping while it runs.  Host tensors in the
+        # same dict (e.g. ``torch.get_rng_state()``) travel to the writer as they are, like in the reference, whose
+        # ``preload_tensors`` maps them through ``.to("cpu")`` = identity (``utils.py:93-94``).
+        cuda = [t for t in tensors if t.is_cuda]
+        snap = SnapshotEngine.get(devices.pop()).snapshot(cuda, narrow=self._narrow)
+        counter = iter(range(len(cuda)))
+
+        def leaf(v):
+            if isinstance(v, torch.Tensor):
+                return SnapshotRef(next(counter)) if v.is_cuda else v.detach()
+            return v
+
+        skeleton = dict_list_map_outplace(leaf, state_dict)
         path, rest = args[0], args[1:]
         request = AsyncRequest(save_snapshot_with_torch, (skeleton, path, snap.descriptor(), *rest), [], kwargs or {})
         idx = self._async_calls_queue.schedule_async_request(request)

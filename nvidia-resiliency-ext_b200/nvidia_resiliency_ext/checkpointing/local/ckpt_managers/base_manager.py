@@ -60,6 +60,7 @@ class BaseCheckpointManager(ABC):
         self.repl_strategy = repl_strategy
         self.session_id = session_id
         self._rank = None
+        self._outstanding = []  # (AsyncRequest, [Snapshot]) of saves that were handed out and not finalized yet
 
     @property
     def rank(self):
@@ -189,6 +190,7 @@ class BaseCheckpointManager(ABC):
             self.latest_iteration < iteration
         ), f"A newer checkpoint is already available: {self.latest_iteration} (saving {iteration})"
         my_id = self._ckpt_id(iteration)
+        self._reap_abandoned()
         snaps = []
         if self.repl_strategy:
             replicas, ids = self.repl_strategy.replicate(state_dict, my_id)
@@ -241,9 +243,66 @@ class BaseCheckpointManager(ABC):
                 for s in snaps:
                     s.wait()
         if is_async:
-            return AsyncRequest(self._save_fn, (to_save, descs), [finalize_fn], async_fn_kwargs={})
+            request = AsyncRequest(self._save_fn, (to_save, descs), [finalize_fn], async_fn_kwargs={})
+            self._outstanding.append((request, snaps))
+            return request
 
-        self._save_fn(to_save, descs)
+        try:
+            self._save_fn(to_save, descs)
+        except BaseException:
+            for s in snaps:  # a failed synchronous save must not keep its pinned slots
+                s.release()
+            raise
         if torch.distributed.is_initialized():
             torch.distributed.barrier()
         finalize_fn()
+
+    def _reap_abandoned(self):
+        """Give back the host slots of earlier asynchronous saves that will never be finalized.
+
+        ``finalize_fn`` releases the slots of a save.  A save whose queue was aborted (``abort_nvrx_checkpoint`` -- the
+        in-process restart path, reference ``inprocess/abort.py:201``) or closed never runs it, and each such save would pin one
+        or two snapshot-sized shm slots for good.  A request is *abandoned* when no live ``AsyncCallsQueue`` holds it any more
+        and its slots are still busy; requests the caller has not scheduled yet (or runs with ``execute_sync``) are kept as long
+        as the caller keeps the request object alive."""
+        if not self._outstanding:
+            return
+        import sys
+
+        from ...async_ckpt.core import AsyncCallsQueue
+
+        scheduled = set()
+        for queue in AsyncCallsQueue.get_instances():
+            for active in list(getattr(queue, "async_calls", ())):
+                for fn in getattr(getattr(active, "async_request", None), "finalize_fns", ()) or ():
+                    scheduled.add(id(fn))
+        keep = []
+        for request, snaps in self._outstanding:
+            if all(s.released for s in snaps):
+                continue  # finalized
+            held_by_queue = any(id(fn) in scheduled for fn in request.finalize_fns)
+            was_scheduled = any(getattr(fn, "nvrx_scheduled", False) for fn in request.finalize_fns)
+            # not scheduled yet: the caller may still do so while it holds the request (references: the tuple in
+            # self._outstanding, the loop variable, getrefcount's argument)
+            pending_at_caller = not was_scheduled and sys.getrefcount(request) > 3
+            if held_by_queue or pending_at_caller:
+                keep.append((request, snaps))
+                continue
+            logger.warning("local checkpoint save was never finalized (aborted queue?): releasing its host snapshot slots")
+            for s in snaps:
+                s.release()
+        self._outstanding = keep
+
+    def release_unfinalized(self):
+        """Release the host slots of every save of this manager that has not been finalized (call after aborting the queue,
+        e.g. from an in-process restart handler).  The saves themselves are lost, like in the reference."""
+        for _, snaps in self._outstanding:
+            for s in snaps:
+                s.release()
+        self._outstanding = []
+
+    def __del__(self):
+        try:
+            self.release_unfinalized()
+        except Exception:  # noqa: BLE001
+            pass

@@ -147,6 +147,7 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
             f"A newer checkpoint is already available: {self.latest_iteration} (saving {iteration})"
         )
         my_id = self._ckpt_id(iteration)
+        self._reap_abandoned()  # slots of saves whose queue was aborted (base_manager)
         payload = list(state_dict.pop_tensors())
         skeleton_blob = pickle.dumps(state_dict)  # hollow: a few KB, stored with every fragment
         on_gpu = any(t.is_cuda for t in payload)
@@ -185,8 +186,15 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
                 s.wait()
         args = ({my_id: state_dict}, descs, frag_specs)
         if is_async:
-            return AsyncRequest(self._save_sharded_fn, args, [finalize_fn], async_fn_kwargs={})
-        self._save_sharded_fn(*args)
+            request = AsyncRequest(self._save_sharded_fn, args, [finalize_fn], async_fn_kwargs={})
+            self._outstanding.append((request, snaps))
+            return request
+        try:
+            self._save_sharded_fn(*args)
+        except BaseException:
+            for s in snaps:
+                s.release()
+            raise
         if dist.is_initialized():
             dist.barrier()
         finalize_fn()
