@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define NVRX_ABI_VERSION 1
+#define NVRX_ABI_VERSION 2
 
 enum {
     NVRX_OK = 0,
@@ -138,15 +138,28 @@ int nvrx_pack_broadcast(nvrx_plan* plan, void* const* peer_bases, int n_peers, u
 int nvrx_drain(void* host_dst, const void* staging, uint64_t bytes, uint64_t chunk_bytes,
                volatile uint64_t* progress, uint64_t base_value, void* stream, void* done_event);
 /* Pipelined pack + drain, the whole snapshot in one call: the packed range is cut into `chunk_bytes` chunks; chunk c is
- * packed by its own sub-launch on `pack_stream` (tiles in staging order) and copied to `host_dst` on `drain_stream` as
- * soon as that sub-launch has finished, so the D2H starts ~100 us after the call instead of after the full pack.
+ * copied to `host_dst` on `drain_stream` as soon as the pack sub-launch (on `pack_stream`, tiles in staging order) that
+ * covers it has finished, so the D2H starts ~100 us after the call instead of after the full pack.
  * `progress`/`base_value` as in nvrx_drain.  `packed_event` (optional) is recorded on pack_stream after the last
  * sub-launch -- the training stream is free from there; `done_event` (optional) on drain_stream after the last copy. */
 int nvrx_snapshot(nvrx_plan* plan, void* staging, void* host_dst, uint64_t chunk_bytes, volatile uint64_t* progress,
                   uint64_t base_value, void* pack_stream, void* drain_stream, void* packed_event, void* done_event);
+/* Kernel launches of the last nvrx_snapshot on this plan: the pack runs as a few sub-launches over geometrically growing
+ * groups of copy chunks (1, 4, 16, ... chunks; NVRX_B200_PACK_GROWTH), 4 for a 16 GB snapshot with 256 MiB chunks. */
+int nvrx_plan_last_launches(const nvrx_plan* plan, uint32_t* launches);
 /* Mirror for restore: pinned host -> device staging (H2D), optional event. */
 int nvrx_fill(void* staging, const void* host_src, uint64_t bytes, uint64_t chunk_bytes, void* stream,
               void* done_event);
+
+/* Restore pipeline, file -> device staging without a snapshot-sized host buffer: `threads` readers pread() the n extents
+ * (file_offs[i], nbytes[i]) of `fd` into a process-wide ring of `ring_slots` pinned chunks of `chunk_bytes` (allocated on
+ * first use per device; 0 / <2 = defaults 64 MiB x 4) at the staging positions stg_offs[i] (ascending, disjoint), and the
+ * calling thread copies every chunk to `staging` on `stream` as soon as its reads have landed, so the file read and the H2D
+ * overlap.  Returns when the last chunk's copy has left the ring; follow with nvrx_scatter on the same stream.
+ * Replaces the reference's torch.load + N x tensor.to("cuda") (local_manager.py:91-105, basic_state_dict.py:184-187). */
+int nvrx_fill_from_fd(void* staging, uint64_t staging_bytes, int fd, int64_t n, const uint64_t* stg_offs,
+                      const uint64_t* nbytes, const uint64_t* file_offs, uint64_t chunk_bytes, int ring_slots, int threads,
+                      int device, void* stream);
 
 /* ---- device staging / stream helpers (so callers need no CUDA binding of their own) ---------- */
 int nvrx_dev_alloc(int device, uint64_t bytes, void** out); /* cudaMalloc, zero-filled, IPC-capable */

@@ -79,6 +79,7 @@ struct nvrx_plan {
     bool segs_dirty = true, tiles_dirty = true;
     std::vector<cudaEvent_t> chunk_events;  // pack -> drain hand-off of the pipelined snapshot
     cudaEvent_t upload_done = nullptr;      // last H2D of the descriptor mirrors (they are reused)
+    uint32_t last_launches = 0;             // kernel launches of the last nvrx_snapshot (its pack groups)
 };
 
 namespace {
@@ -592,13 +593,22 @@ int nvrx_snapshot(nvrx_plan* p, void* staging, void* host_dst, uint64_t chunk_by
     if (progress) NVRX_CUDA(cudaHostGetDevicePointer(&prog_dev, const_cast<uint64_t*>(progress), 0));
     PeerMap pm;
     memset(&pm, 0, sizeof(pm));
+    // Pack sub-launches cover GROUPS of copy chunks that grow geometrically (1, g, g^2, ... chunks; g = 4 by default,
+    // NVRX_B200_PACK_GROWTH, 1 = one launch per chunk): the pack runs ~55x faster than the PCIe copy, so the copy of group
+    // k (which must wait for that group's launch) never waits on the pack of group k+1 as long as g < 55, and a 16 GB
+    // snapshot needs 4 launches instead of 60 -- no launch gaps and CTA tails on the training stream.  The copies themselves
+    // stay `chunk_bytes` long (granularity of the progress word the writer follows).
+    uint64_t growth = 4;
+    if (const char* env = getenv("NVRX_B200_PACK_GROWTH")) growth = std::max<long long>(1, atoll(env));
     uint32_t b_lo = 0, r_lo = p->n_bulk;
-    for (uint64_t c = 0; c < n_chunks; ++c) {
-        const uint64_t end_pos = std::min(total, (c + 1) * chunk_bytes);
-        // chunk c = every tile that STARTS before end_pos and was not launched yet; a tile reaching into chunk c+1
-        // is complete before chunk c+1's event, which is what that chunk's copy waits for
-        const uint32_t b_hi = (c + 1 == n_chunks) ? p->n_bulk : lower_tile(p, b_lo, p->n_bulk, end_pos);
-        const uint32_t r_hi = (c + 1 == n_chunks) ? p->n_tiles : lower_tile(p, r_lo, p->n_tiles, end_pos);
+    uint64_t c = 0, group = 1, n_groups = 0;
+    while (c < n_chunks) {
+        const uint64_t g_end = std::min(n_chunks, c + group);
+        const uint64_t end_pos = std::min(total, g_end * chunk_bytes);
+        // group = every tile that STARTS before end_pos and was not launched yet; a tile reaching into the next group
+        // is complete before that group's event, which is what that group's copies wait for
+        const uint32_t b_hi = (g_end == n_chunks) ? p->n_bulk : lower_tile(p, b_lo, p->n_bulk, end_pos);
+        const uint32_t r_hi = (g_end == n_chunks) ? p->n_tiles : lower_tile(p, r_lo, p->n_tiles, end_pos);
         TileSpan span;
         span.a = p->d_tiles + b_lo;
         span.na = b_hi - b_lo;
@@ -608,22 +618,33 @@ int nvrx_snapshot(nvrx_plan* p, void* staging, void* host_dst, uint64_t chunk_by
         if (rc) return rc;
         b_lo = b_hi;
         r_lo = r_hi;
-        NVRX_CUDA(cudaEventRecord(p->chunk_events[c], ps));
-        NVRX_CUDA(cudaStreamWaitEvent(ds, p->chunk_events[c], 0));
-        const uint64_t begin = c * chunk_bytes;
-        NVRX_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(host_dst) + begin, static_cast<const uint8_t*>(staging) + begin,
-                                  end_pos - begin, cudaMemcpyDeviceToHost, ds));
-        if (prog_dev) {
-            rc = nvrx_stream_write_u64(ds, prog_dev, base_value + end_pos);
-            if (rc) return rc;
+        NVRX_CUDA(cudaEventRecord(p->chunk_events[n_groups], ps));
+        NVRX_CUDA(cudaStreamWaitEvent(ds, p->chunk_events[n_groups], 0));
+        ++n_groups;
+        for (; c < g_end; ++c) {
+            const uint64_t begin = c * chunk_bytes, stop = std::min(total, (c + 1) * chunk_bytes);
+            NVRX_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(host_dst) + begin, static_cast<const uint8_t*>(staging) + begin,
+                                      stop - begin, cudaMemcpyDeviceToHost, ds));
+            if (prog_dev) {
+                rc = nvrx_stream_write_u64(ds, prog_dev, base_value + stop);
+                if (rc) return rc;
+            }
         }
+        group *= growth;
     }
+    p->last_launches = static_cast<uint32_t>(n_groups);
     if (n_chunks == 0 && prog_dev) {
         rc = nvrx_stream_write_u64(ds, prog_dev, base_value);
         if (rc) return rc;
     }
     if (packed_event) NVRX_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(packed_event), ps));
     if (done_event) NVRX_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(done_event), ds));
+    return NVRX_OK;
+}
+
+int nvrx_plan_last_launches(const nvrx_plan* p, uint32_t* launches) {
+    if (!p || !launches) return NVRX_E_INVALID;
+    *launches = p->last_launches;
     return NVRX_OK;
 }
 

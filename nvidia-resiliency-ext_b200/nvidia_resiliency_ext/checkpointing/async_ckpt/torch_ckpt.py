@@ -36,12 +36,13 @@ class TorchAsyncCheckpoint(object):
         self._reap()
         tensors = []
         _collect_tensors(state_dict, tensors)
-        if not any(t.is_cuda for t in tensors):
+        cuda = [t for t in tensors if t.is_cuda]
+        if not cuda:
             # nothing on the GPU (reference config C1): the host tensors go to the writer as they are
             request = AsyncRequest(TorchAsyncCheckpoint.async_fn, (preload_tensors(state_dict), *args), [], kwargs or {})
             self._async_calls_queue.schedule_async_request(request)
             return
-        devices = {t.device.index for t in tensors if t.is_cuda}
+        devices = {t.get_device() for t in cuda}
         if len(devices) != 1:
             raise ValueError("async_save: the CUDA tensors of the state dict must live on one device")
         from ..b200.engine import SnapshotEngine
@@ -49,7 +50,6 @@ class TorchAsyncCheckpoint(object):
         # GPU work first (pack sub-launches + drain are enqueued here), Python bookkeeping while it runs.  Host tensors in the
         # same dict (e.g. ``torch.get_rng_state()``) travel to the writer as they are, like in the reference, whose
         # ``preload_tensors`` maps them through ``.to("cpu")`` = identity (``utils.py:93-94``).
-        cuda = [t for t in tensors if t.is_cuda]
         snap = SnapshotEngine.get(devices.pop()).snapshot(cuda, narrow=self._narrow)
         counter = iter(range(len(cuda)))
 

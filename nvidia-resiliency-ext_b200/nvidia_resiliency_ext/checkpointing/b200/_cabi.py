@@ -12,7 +12,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK = 0
 E_INVALID = 1000
@@ -48,7 +48,9 @@ EXPORTED_SYMBOLS = (
     "nvrx_pack_broadcast",
     "nvrx_drain",
     "nvrx_snapshot",
+    "nvrx_plan_last_launches",
     "nvrx_fill",
+    "nvrx_fill_from_fd",
     "nvrx_dev_alloc",
     "nvrx_dev_free",
     "nvrx_stream_create",
@@ -136,7 +138,9 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_pack_broadcast": (_int, [_vp, P(_vp), _int, _u64, _vp]),
         "nvrx_drain": (_int, [_vp, _vp, _u64, _u64, _vp, _u64, _vp, _vp]),
         "nvrx_snapshot": (_int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]),
+        "nvrx_plan_last_launches": (_int, [_vp, P(_u32)]),
         "nvrx_fill": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
+        "nvrx_fill_from_fd": (_int, [_vp, _u64, _int, _i64, P(_u64), P(_u64), P(_u64), _u64, _int, _int, _int, _vp]),
         "nvrx_dev_alloc": (_int, [_int, _u64, P(_vp)]),
         "nvrx_dev_free": (_int, [_int, _vp]),
         "nvrx_stream_create": (_int, [_int, _int, P(_vp)]),

@@ -110,6 +110,11 @@ class Plan:
         check(self._lib.nvrx_plan_tiles(self._h, shard_bytes, C.byref(nb), C.byref(nt), seg, nby, off, n), "nvrx_plan_tiles")
         return nb.value, [(seg[i], nby[i], off[i]) for i in range(n)]
 
+    def last_launches(self) -> int:
+        n = C.c_uint32()
+        check(self._lib.nvrx_plan_last_launches(self._h, C.byref(n)), "nvrx_plan_last_launches")
+        return n.value
+
     def set_variant(self, variant: int) -> None:
         check(self._lib.nvrx_plan_set_variant(self._h, variant), "nvrx_plan_set_variant")
 
@@ -646,6 +651,7 @@ class SnapshotEngine:
         self._slot_gen = 0
         self.launches = 0  # kernels launched by this engine (pack + scatter)
         self.resident_restores = 0  # restores that read a published slot in place (no host copy)
+        self.file_restores = 0  # restores fed straight from the checkpoint file through the pinned ring
         self._aux: Optional[Stream] = None  # checksum kernels (created on first use)
         self._pid = os.getpid()  # forked writers inherit this object; only the creator may tear it down
 
@@ -741,15 +747,20 @@ class SnapshotEngine:
         geometry of ``ptzip.slot_offsets`` (room for a ZIP local header in front of every segment) instead of the dense
         default, so that the drained slot can be published as a file without a copy.  ``offsets``: explicit staging
         offsets (restore straight from a published slot)."""
-        key = tuple((t.numel() * t.element_size(), t.dtype, nr) for t, nr in zip(tensors, narrow))
+        nbytes = [t.nbytes for t in tensors]
+        dtypes = [t.dtype for t in tensors]
+        if narrow is not None and not any(narrow):
+            narrow = None
+        key = (tuple(nbytes), tuple(dtypes), tuple(narrow) if narrow is not None else None)
         if offsets is not None:
             key = ("at", tuple(offsets)) + key
         elif container:
             key = ("container",) + key
-        ptrs = [t.data_ptr() if t.numel() else 0 for t in tensors]
+        ptrs = [t.data_ptr() if nb else 0 for t, nb in zip(tensors, nbytes)]
         plan = self._plans.get(key)
         if plan is None:
-            nbytes = [t.numel() * t.element_size() for t in tensors]
+            if narrow is None:
+                narrow = [False] * len(tensors)
             flags = [_cabi.SEG_NARROW_F32_BF16 if nr else 0 for nr in narrow]
             if offsets is None and container:
                 from .ptzip import slot_offsets
@@ -774,13 +785,19 @@ class SnapshotEngine:
 
         Returns as soon as the pack kernel and the side-stream copy are *enqueued*.  ``container`` (default: the
         ``NVRX_B200_ZERO_COPY`` switch) packs in checkpoint-container geometry, see :meth:`_plan_for`."""
-        all_tensors = list(tensors)
-        passthrough = {i: t for i, t in enumerate(all_tensors) if not (t.is_cuda and t.device.index == self.device)}
-        cuda_tensors = [t for i, t in enumerate(all_tensors) if i not in passthrough] if passthrough else all_tensors
+        all_tensors = tensors if isinstance(tensors, list) else list(tensors)
+        dev = self.device
+        # everything up to the launch is on the training stream's critical path (the stall): one cheap test for the common
+        # case (all tensors on this device, contiguous), the general bookkeeping only when it fails
+        passthrough: Dict[int, torch.Tensor] = {}
+        cuda_tensors = all_tensors
+        if not all([t.get_device() == dev for t in all_tensors]):
+            passthrough = {i: t for i, t in enumerate(all_tensors) if t.get_device() != dev}
+            cuda_tensors = [t for i, t in enumerate(all_tensors) if i not in passthrough]
         # the kernel walks contiguous byte ranges; strided tensors are compacted first (rare)
-        if not all(t.is_contiguous() for t in cuda_tensors):
+        if not all([t.is_contiguous() for t in cuda_tensors]):
             cuda_tensors = [t if t.is_contiguous() else t.detach().contiguous() for t in cuda_tensors]
-        mask = self._narrow_mask(cuda_tensors, narrow)
+        mask = self._narrow_mask(cuda_tensors, narrow) if narrow else None
         if container is None:
             from .fastsave import zero_copy_enabled
 
@@ -842,7 +859,7 @@ class SnapshotEngine:
                 ),
                 "nvrx_snapshot",
             )
-        self.launches += (-(-plan.staging_bytes // self.drain_chunk) if not self.timing else 1) if plan.n_tiles else 0
+        self.launches += (plan.last_launches() if not self.timing else 1) if plan.n_tiles else 0
         slot.drained_total = base + plan.staging_bytes
         self._staging_free = slot.done_event
         crc_info = None
@@ -863,15 +880,23 @@ class SnapshotEngine:
             self._staging_free = free_ev
             crc_info = {"offset": crc_off, "n_values": crc.n_values, "ready_offset": ready_off, "ready_value": slot.drained_total}
 
-        layout = PackedLayout(
-            shapes=[tuple(t.shape) for t in cuda_tensors],
-            dtypes=[dtype_name(torch.bfloat16 if nr else t.dtype) for t, nr in zip(cuda_tensors, mask)],
-            src_dtypes=[dtype_name(t.dtype) for t in cuda_tensors],
-            offsets=list(plan.offsets),
-            packed_nbytes=list(plan.packed_nbytes),
-            total_bytes=plan.staging_bytes,
-            align=self.align,
-        )
+        # the layout only depends on the plan and the shapes: built once per (plan, shapes), not per snapshot
+        shapes = [t.shape for t in cuda_tensors]
+        cached = plan.__dict__.get("_layout")
+        if cached is not None and cached[0] == shapes:
+            layout = cached[1]
+        else:
+            layout = PackedLayout(
+                shapes=[tuple(sh) for sh in shapes],
+                dtypes=[dtype_name(torch.bfloat16 if (mask is not None and nr) else t.dtype)
+                        for t, nr in zip(cuda_tensors, mask if mask is not None else [False] * len(cuda_tensors))],
+                src_dtypes=[dtype_name(t.dtype) for t in cuda_tensors],
+                offsets=list(plan.offsets),
+                packed_nbytes=list(plan.packed_nbytes),
+                total_bytes=plan.staging_bytes,
+                align=self.align,
+            )
+            plan.__dict__["_layout"] = (shapes, layout)
         return Snapshot(
             engine=self, slot=slot, layout=layout, progress_target=slot.drained_total, passthrough=passthrough,
             n_total=len(all_tensors), pack_start=start, pack_stop=stop, crc_info=crc_info,
@@ -912,6 +937,8 @@ class SnapshotEngine:
             out = list(out)
             for o, t, td in zip(out, host_tensors, target_dtypes):
                 assert o.is_cuda and o.is_contiguous() and o.dtype == td and o.shape == t.shape
+        if resident is None and file_source is not None and not (expect_crcs is not None and any(expect_crcs)):
+            return self._restore_from_file(out, mask, file_source)
         if resident is not None:
             slot, offsets = resident
             plan = self._plan_for(out, mask, offsets=list(offsets))
@@ -972,6 +999,42 @@ class SnapshotEngine:
                     )
         finally:
             self._release(slot)
+        return out
+
+    RESTORE_CHUNK = int(os.environ.get("NVRX_B200_RESTORE_CHUNK_MB", "64")) << 20
+    RESTORE_RING = int(os.environ.get("NVRX_B200_RESTORE_RING", "4"))
+    RESTORE_THREADS = int(os.environ.get("NVRX_B200_RESTORE_THREADS", "0"))
+
+    def _restore_from_file(self, out: List[torch.Tensor], mask: Sequence[bool], file_source) -> List[torch.Tensor]:
+        """File -> GPU tensors without a snapshot-sized host buffer (``nvrx_fill_from_fd``): a pool of readers fills a small
+        ring of pinned chunks from the checkpoint file while the chunks already read travel to the device; one scatter
+        kernel at the end.  A freshly restarted process does not have to create and page-lock a 16 GB slot first (~2 s)."""
+        path, file_offs = file_source
+        plan = self._plan_for(out, mask)
+        staging = self._ensure_staging(plan.staging_bytes)
+        live = [(off, nb, fo) for off, nb, fo in zip(plan.offsets, plan.packed_nbytes, file_offs) if nb]
+        stream = self._current_stream()
+        if self._staging_free is not None:
+            stream_wait_event(stream, self._staging_free)
+        threads = self.RESTORE_THREADS or max(self.prefault_threads, min(32, os.cpu_count() or 1))
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            check(
+                self.lib.nvrx_fill_from_fd(
+                    staging.ptr, plan.staging_bytes, fd, len(live), _u64_array([x[0] for x in live]), _u64_array([x[1] for x in live]),
+                    _u64_array([x[2] for x in live]), self.RESTORE_CHUNK, self.RESTORE_RING, threads, self.device, stream,
+                ),
+                "nvrx_fill_from_fd",
+            )
+        finally:
+            os.close(fd)
+        plan.scatter(staging.ptr, stream)
+        self.launches += 1 if plan.n_tiles else 0
+        self.file_restores += 1
+        done = Event(self.device)
+        done.record(stream)
+        self._staging_free = done
+        done.synchronize()  # restore is a blocking call like the reference's
         return out
 
     def resident_source(self, path, host_tensors: Sequence[torch.Tensor]) -> Optional[Tuple[_Slot, List[int]]]:

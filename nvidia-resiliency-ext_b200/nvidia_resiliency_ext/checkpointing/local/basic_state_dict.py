@@ -156,8 +156,9 @@ class BasicTensorAwareStateDict(TensorAwareStateDict):
 
             if fastsave.zero_copy_enabled():
                 resident = engine.resident_source(source, host)
-            if resident is None and os.environ.get("NVRX_B200_RESTORE_PREAD", "0") == "1":
-                # opt-in (to be measured): fill the pinned slot by parallel pread from the file instead of from its mmap
+            if resident is None and os.environ.get("NVRX_B200_RESTORE_PREAD", "1") != "0":
+                # default: feed the H2D straight from the file through a small pinned ring (parallel pread, chunk-pipelined
+                # with the copy) instead of copying out of the file's mmap into a snapshot-sized pinned slot first
                 offs = ptzip.tensor_offsets_in_file(source, host)
                 file_source = (source, offs) if offs is not None else None
         moved = iter(engine.restore(host, widen_to=widen_to, resident=resident, file_source=file_source, expect_crcs=expect))

@@ -25,6 +25,9 @@ class FakeCudaTensor(torch.Tensor):
     is_cuda = property(lambda self: True)
     device = property(lambda self: torch.device("cuda", 0))
 
+    def get_device(self):
+        return 0
+
     @staticmethod
     def wrap(t: torch.Tensor) -> "FakeCudaTensor":
         return torch.Tensor._make_subclass(FakeCudaTensor, t.detach())
@@ -165,6 +168,17 @@ class FakeDeviceLib:
     def nvrx_fill(self, staging, host, nbytes, chunk, stream, done):
         C.memmove(_val(staging), _val(host), nbytes)
         self.calls.append("fill")
+        return 0
+
+    def nvrx_fill_from_fd(self, staging, staging_bytes, fd, n, stg_offs, nbytes, file_offs, chunk, slots, threads, device, stream):
+        import os
+
+        for i in range(n):
+            if nbytes[i]:
+                data = os.pread(fd, nbytes[i], file_offs[i])
+                assert len(data) == nbytes[i] and stg_offs[i] + nbytes[i] <= staging_bytes
+                C.memmove(_val(staging) + stg_offs[i], data, nbytes[i])
+        self.calls.append("fill_from_fd")
         return 0
 
     def nvrx_snapshot(self, h, staging, host, chunk, progress, base, pack_stream, side, packed_ev, done):

@@ -162,8 +162,15 @@ def test_pread_restore(monkeypatch, built_library, tmp_path, dist_1rank):
 
         monkeypatch.setattr(HostBuffer, "gather", lambda self, *a, **k: gathers.append(1))
         loaded, _ = mgr.load()
-        assert not gathers  # the slot was filled by readv_fd, not by the mmap gather
+        assert not gathers and engine.file_restores == 1  # file -> pinned ring -> staging (nvrx_fill_from_fd), no slot, no mmap gather
+        assert "fill_from_fd" in lib.calls and not any(s.busy for s in engine._slots)
         _same(loaded.state_dict, _state(5, wrap=False))
+        # opt-out: the mmap gather into a pinned slot
+        monkeypatch.setenv("NVRX_B200_RESTORE_PREAD", "0")
+        mgr2 = LocalCheckpointManager(tmp_path)
+        assert mgr2.find_latest() == 9
+        loaded, _ = mgr2.load()
+        assert gathers and engine.file_restores == 1
 
 
 def test_dcp_writer_cuda_branch(monkeypatch, built_library, tmp_path, dist_1rank):

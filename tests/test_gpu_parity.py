@@ -242,3 +242,48 @@ def test_full_size_c2_roundtrip_properties(built_library):
     with open("gpurun_out/fullsize_timing.txt", "w") as f:
         for (a, ta), (b, tb) in zip(marks, marks[1:]):
             f.write(f"{b:18s} {tb - ta:8.3f} s\n")
+
+
+@pytest.mark.parametrize("chunk_mb,ring,threads", [(4, 2, 3), (64, 4, 16)])
+def test_fill_from_fd_pipeline_matches_the_file(tmp_path, chunk_mb, ring, threads):
+    """nvrx_fill_from_fd (file -> pinned ring -> device staging): ragged extents at unaligned file offsets, extents larger than
+    a chunk, empty ones, more chunks than ring slots; the device bytes of every extent equal the file's, bit for bit."""
+    import ctypes as C
+    import os
+
+    from nvidia_resiliency_ext.checkpointing.b200 import _cabi
+
+    rng = np.random.default_rng(chunk_mb)
+    blob = rng.integers(0, 256, size=40 << 20, dtype=np.uint8)
+    path = tmp_path / "blob.bin"
+    blob.tofile(path)
+    sizes = [0, 1, 15, 16, 4097, 1 << 20, (5 << 20) + 3, 0, 512, (9 << 20) + 1, 77, 3 << 20]
+    file_offs, stg_offs, cur_f, cur_s = [], [], 13, 0
+    for s in sizes:
+        file_offs.append(cur_f)
+        cur_s = (cur_s + 511) // 512 * 512
+        stg_offs.append(cur_s)
+        cur_f += s + 7
+        cur_s += s
+    total = (cur_s + 511) // 512 * 512
+    stg = torch.full((total,), 0xAB, dtype=torch.uint8, device="cuda")
+    u64 = lambda v: (C.c_uint64 * len(v))(*v)  # noqa: E731
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        for _ in range(2):  # second call reuses the ring
+            _cabi.check(_cabi.lib().nvrx_fill_from_fd(stg.data_ptr(), total, fd, len(sizes), u64(stg_offs), u64(sizes), u64(file_offs),
+                                                      chunk_mb << 20, ring, threads, torch.cuda.current_device(), _stream()), "nvrx_fill_from_fd")
+            torch.cuda.synchronize()
+            got = stg.cpu().numpy()
+            for s, fo, so in zip(sizes, file_offs, stg_offs):
+                assert np.array_equal(got[so : so + s], blob[fo : fo + s]), (s, fo, so)
+    finally:
+        os.close(fd)
+    # a file shorter than the extents say is an error, not garbage
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        rc = _cabi.lib().nvrx_fill_from_fd(stg.data_ptr(), total, fd, 1, u64([0]), u64([4096]), u64([blob.size - 100]), 0, 0, 2,
+                                           torch.cuda.current_device(), _stream())
+        assert rc == _cabi.E_SYS
+    finally:
+        os.close(fd)

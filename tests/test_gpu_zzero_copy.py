@@ -91,8 +91,8 @@ def test_local_manager_zero_copy_roundtrip(shm_dir, dist_1rank, built_library, m
 
 
 def test_restore_through_pread(tmp_path, shm_dir, dist_1rank, built_library, monkeypatch):
-    """NVRX_B200_RESTORE_PREAD=1: the pinned slot is filled by parallel pread from the file (any file system), then the usual
-    one H2D + one scatter kernel."""
+    """Default restore of a local checkpoint: parallel pread from the file (any file system) into the pinned ring, chunk-pipelined
+    H2D (nvrx_fill_from_fd), one scatter kernel."""
     from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
     from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
 
@@ -101,5 +101,9 @@ def test_restore_through_pread(tmp_path, shm_dir, dist_1rank, built_library, mon
         mgr = LocalCheckpointManager(root)
         mgr.save(BasicTensorAwareStateDict(_state(55)), 4, is_async=False)
         assert mgr.find_latest() == 4
+        from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
+
+        before = SnapshotEngine.get().file_restores
         loaded, _ = mgr.load()
         assert _equal(loaded.state_dict, _state(55)) and all(t.is_cuda for t in loaded.tensors)
+        assert SnapshotEngine.get().file_restores == before + 1
