@@ -128,21 +128,60 @@ int build_tiles(nvrx_plan* p) {
     }
     const size_t total = bulk.size() + ragged.size();
     if (total > 0xffffffffull) return NVRX_E_INVALID;
-    if (p->shard_bytes && p->first_shard) {
-        // Rotate both lists so the walk starts with the tiles of shard `first_shard` and wraps around.  CTAs take
-        // tiles in list order, so list order is time order: giving every rank a different starting shard keeps the
-        // ranks of a clique from storing into the same destination GPU at the same time (NVLink incast).
-        const uint64_t start = static_cast<uint64_t>(p->first_shard) * p->shard_bytes;
+    if (p->shard_bytes) {
         auto pos_of = [&](const TileDesc& t) {
             const bool nr = (p->flags[t.seg] & NVRX_SEG_NARROW_F32_BF16) != 0;
             return p->off[t.seg] + (nr ? t.off / 2 : t.off);
         };
-        auto rot = [&](std::vector<TileDesc>& v) {
-            auto it = std::partition_point(v.begin(), v.end(), [&](const TileDesc& t) { return pos_of(t) < start; });
-            std::rotate(v.begin(), it, v.end());
-        };
-        rot(bulk);
-        rot(ragged);
+        const char* env = getenv("NVRX_B200_SHARD_INTERLEAVE");
+        const bool interleave = !(env && env[0] == '0');
+        if (interleave) {
+            // Destination-major balance for the fused pack + all-to-all: list position q holds a tile of shard
+            // (first_shard + q) mod n_shards.  CTAs take list positions b, b+G, b+2G, ..., so at every moment the CTAs of
+            // this GPU are spread evenly over ALL destination GPUs (each peer gets 1/n of this GPU's NVLink egress, and
+            // receives 1/n from each of its n senders) -- no destination sees more than one GPU's worth of ingress, whatever
+            // the relative progress of the ranks.  Walking the shards one after the other made every rank store into the
+            // same one or two peers at a time (incast: 228 GB/s per GPU at 8 GPUs, profiles/r01_c4_kernel_only_8gpu.json).
+            auto weave = [&](std::vector<TileDesc>& v) {
+                if (v.empty()) return;
+                const uint64_t n_shards = (p->staging_bytes + p->shard_bytes - 1) / p->shard_bytes;
+                if (n_shards < 2) return;
+                std::vector<size_t> begin(n_shards + 1, v.size());  // v is sorted by staging position
+                size_t i = 0;
+                for (uint64_t sh = 0; sh < n_shards; ++sh) {
+                    while (i < v.size() && pos_of(v[i]) / p->shard_bytes < sh) ++i;
+                    begin[sh] = i;
+                }
+                begin[n_shards] = v.size();
+                for (uint64_t sh = n_shards; sh-- > 0;) begin[sh] = std::min(begin[sh], begin[sh + 1]);
+                std::vector<TileDesc> out;
+                out.reserve(v.size());
+                std::vector<size_t> cur(begin.begin(), begin.end() - 1);
+                size_t left = v.size();
+                uint64_t sh = p->first_shard % n_shards;
+                while (left) {
+                    if (cur[sh] < begin[sh + 1]) {
+                        out.push_back(v[cur[sh]++]);
+                        --left;
+                    }
+                    sh = (sh + 1 == n_shards) ? 0 : sh + 1;
+                }
+                v.swap(out);
+            };
+            weave(bulk);
+            weave(ragged);
+        } else if (p->first_shard) {
+            // Sequential walk, rotated so that it starts with the tiles of shard `first_shard` and wraps around: with a
+            // different starting shard on every rank the ranks of a clique store into distinct peers as long as they stay
+            // in step (kept for the A/B measurement, NVRX_B200_SHARD_INTERLEAVE=0).
+            const uint64_t start = static_cast<uint64_t>(p->first_shard) * p->shard_bytes;
+            auto rot = [&](std::vector<TileDesc>& v) {
+                auto it = std::partition_point(v.begin(), v.end(), [&](const TileDesc& t) { return pos_of(t) < start; });
+                std::rotate(v.begin(), it, v.end());
+            };
+            rot(bulk);
+            rot(ragged);
+        }
     }
     p->h_tiles.clear();
     p->h_tiles.reserve(total);
@@ -472,6 +511,7 @@ int nvrx_plan_tiles(const nvrx_plan* p, uint64_t shard_bytes, uint32_t* n_bulk, 
         tmp.nbytes = p->nbytes;
         tmp.off = p->off;
         tmp.flags = p->flags;
+        tmp.staging_bytes = p->staging_bytes;
         tmp.shard_bytes = shard_bytes;
         tmp.first_shard = p->first_shard;
         int rc = build_tiles(&tmp);

@@ -600,7 +600,7 @@ class AsyncCallsQueue(metaclass=ObjectTracker):
         async_request = async_request.freeze()
         for fn in async_request.finalize_fns:
             try:
-                fn.nvrx_scheduled = True  # lets the owner of pinned snapshot slots tell "aborted" from "not scheduled yet"
+                fn.scheduled_by_queue = True  # lets the owner of pinned snapshot slots tell "aborted" from "not scheduled yet"
             except AttributeError:
                 pass
         # finalize functions stay on the trainer: they are closures over managers / process groups

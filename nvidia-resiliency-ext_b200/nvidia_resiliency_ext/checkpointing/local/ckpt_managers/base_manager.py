@@ -281,7 +281,7 @@ class BaseCheckpointManager(ABC):
             if all(s.released for s in snaps):
                 continue  # finalized
             held_by_queue = any(id(fn) in scheduled for fn in request.finalize_fns)
-            was_scheduled = any(getattr(fn, "nvrx_scheduled", False) for fn in request.finalize_fns)
+            was_scheduled = any(getattr(fn, "scheduled_by_queue", False) for fn in request.finalize_fns)
             # not scheduled yet: the caller may still do so while it holds the request (references: the tuple in
             # self._outstanding, the loop variable, getrefcount's argument)
             pending_at_caller = not was_scheduled and sys.getrefcount(request) > 3

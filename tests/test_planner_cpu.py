@@ -35,8 +35,16 @@ def check_cover(plan, ptrs, nbytes, flags, tile_bytes, shard_bytes=0):
             assert lo == cur, f"segment {seg}: gap or overlap at {lo} (expected {cur})"
             cur = hi
         assert cur == nbytes[seg]
-    # both lists are sorted by staging position (the pipelined snapshot bisects them)
+    # both lists are sorted by staging position (the pipelined snapshot bisects them); sharded plans interleave the shards
+    # (destination-major order of the fused exchange) and are only sorted inside a shard
     pos = lambda t: plan.offsets[t[0]] + (t[2] // 2 if (flags and flags[t[0]]) else t[2])  # noqa: E731
+    if shard_bytes:
+        for part in (tiles[:n_bulk], tiles[n_bulk:]):
+            by_shard = {}
+            for t in part:
+                by_shard.setdefault(pos(t) // shard_bytes, []).append(pos(t))
+            assert all(v == sorted(v) for v in by_shard.values())
+        return
     assert [pos(t) for t in tiles[:n_bulk]] == sorted(pos(t) for t in tiles[:n_bulk])
     assert [pos(t) for t in tiles[n_bulk:]] == sorted(pos(t) for t in tiles[n_bulk:])
     return n_bulk, tiles
@@ -139,8 +147,38 @@ def test_planner_rejects_bad_arguments(built_library):
     p.close()
 
 
-def test_shard_rotation_only_reorders(built_library):
-    """nvrx_plan_set_shard_rotation: same tiles, walk starts at the requested shard and wraps (per list)."""
+def test_shard_interleave_spreads_every_window_over_all_shards(built_library, monkeypatch):
+    """Default order of a sharded plan (fused pack + all-to-all): list position q holds a tile of shard (first + q) mod n while
+    every shard still has tiles, so any window of CTAs stores to all destination GPUs at once; same tiles as the plain order."""
+    monkeypatch.delenv("NVRX_B200_SHARD_INTERLEAVE", raising=False)
+    nbytes = [3 << 20, 100, 5 << 20, 4, 1 << 20, 7 << 20]
+    ptrs = [0x7F0000000000 + i * (16 << 20) for i in range(len(nbytes))]
+    plan = plan_for(ptrs, nbytes, tile_bytes=32768)
+    total = plan.staging_bytes
+    n = 7
+    shard = orc.shard_bounds(total, n, 512)[0]
+    pos = lambda t: plan.offsets[t[0]] + t[2]  # noqa: E731
+    monkeypatch.setenv("NVRX_B200_SHARD_INTERLEAVE", "0")
+    nb0, base = plan.tiles(shard)
+    monkeypatch.delenv("NVRX_B200_SHARD_INTERLEAVE")
+    for first in (0, 3, 6):
+        plan.set_shard_rotation(first)
+        nb, tiles = plan.tiles(shard)
+        assert nb == nb0 and sorted(tiles) == sorted(base)
+        shards = [pos(t) // shard for t in tiles[:nb]]
+        per_shard = min(shards.count(s) for s in range(n))
+        head = shards[: per_shard * n]  # while every shard still has tiles the walk is a strict round robin
+        assert head == [(first + q) % n for q in range(len(head))]
+        for s in range(n):  # inside a shard the tiles keep their staging order
+            mine = [pos(t) for t in tiles[:nb] if pos(t) // shard == s]
+            assert mine == sorted(mine)
+    plan.set_shard_rotation(0)
+    plan.close()
+
+
+def test_shard_rotation_only_reorders(built_library, monkeypatch):
+    """nvrx_plan_set_shard_rotation with NVRX_B200_SHARD_INTERLEAVE=0: same tiles, walk starts at the requested shard and wraps."""
+    monkeypatch.setenv("NVRX_B200_SHARD_INTERLEAVE", "0")
     nbytes = [3 << 20, 100, 5 << 20, 4, 1 << 20]
     ptrs = [0x7F0000000000 + i * (16 << 20) for i in range(len(nbytes))]
     plan = plan_for(ptrs, nbytes, tile_bytes=32768)

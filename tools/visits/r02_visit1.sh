@@ -1,5 +1,6 @@
 set -u
 mkdir -p gpurun_out/v1
+make -C nvidia-resiliency-ext_b200/csrc -j8 > gpurun_out/v1/build.log 2>&1 || { tail -20 gpurun_out/v1/build.log; exit 1; }
 bash tools/gpu_round.sh tests
 cp gpurun_out/pytest_gpu.log gpurun_out/v1/pytest_gpu_default.log
 NVRX_B200_TEST_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_zcrc.py tests/test_gpu_zzero_copy.py tests/test_gpu_zdcp.py -m gpu -q --timeout=600 > gpurun_out/v1/pytest_gated.log 2>&1
