@@ -377,17 +377,43 @@ def slot_is_published(slot_path: str) -> bool:
 
 
 def tensor_offsets_in_file(path, tensors: Sequence[torch.Tensor]) -> Optional[List[int]]:
-    """File offsets of the data of ``tensors`` -- what ``torch.load(path, mmap=True)`` returned, in record order -- or None
-    when they are not one-record-per-tensor views of a single mapping of that file, ascending, 16-byte aligned."""
+    """File offsets of the data of ``tensors`` -- tensors ``torch.load(path, mmap=True)`` returned, in ascending file order --
+    or None when they are not views of the data records of one mapping of that file, ascending and 16-byte aligned.
+
+    The usual case is one record per tensor in order (``data/i`` is tensor i); objects that pickle other storages first (a host
+    tensor in the ``common`` part of a Megatron-style state dict) shift the numbering, so the general rule is: there is ONE
+    base address such that every tensor starts at ``base + offset of some data record`` that is large enough."""
     live = [(i, t) for i, t in enumerate(tensors) if t.numel()]
     if not live or any(t.is_cuda or not t.is_contiguous() for _, t in live):
         return None
     try:
         reader = torch._C.PyTorchFileReader(os.fspath(path))
         first_i, first_t = live[0]
-        base = first_t.data_ptr() - reader.get_record_offset(f"data/{first_i}")  # address the file is mapped at
-        for i, t in live:
-            if reader.get_record_offset(f"data/{i}") != t.data_ptr() - base:
+        base = None
+        if reader.has_record(f"data/{first_i}"):
+            guess = first_t.data_ptr() - reader.get_record_offset(f"data/{first_i}")  # address the file is mapped at
+            if all(reader.has_record(f"data/{i}") and reader.get_record_offset(f"data/{i}") == t.data_ptr() - guess for i, t in live):
+                base = guess
+        if base is None:
+            recs = {}
+            for name in reader.get_all_records():
+                if name.startswith("data/"):
+                    recs[reader.get_record_offset(name)] = reader.get_record_size(name) if hasattr(reader, "get_record_size") else None
+            need = first_t.numel() * first_t.element_size()
+            for off0, size0 in sorted(recs.items()):
+                if size0 is not None and size0 < need:
+                    continue
+                guess = first_t.data_ptr() - off0
+                ok = True
+                for _, t in live:
+                    size = recs.get(t.data_ptr() - guess, -1)
+                    if size == -1 or (size is not None and size < t.numel() * t.element_size()):
+                        ok = False
+                        break
+                if ok:
+                    base = guess
+                    break
+            if base is None:
                 return None
     except (RuntimeError, OSError):
         return None

@@ -103,9 +103,40 @@ class BaseCheckpointManager(ABC):
     @debug_time("BaseCheckpointManager._load_fn", logger)
     def _load_fn(self, ckpt_id: CkptID) -> TensorAwareStateDict:
         state_dict = self._load(ckpt_id)
-        state_dict.restore_tensor_device(non_blocking=False)
+        if not self._restore_through_engine(state_dict):
+            state_dict.restore_tensor_device(non_blocking=False)
         logger.debug(f"Finish loading {ckpt_id}")
         return state_dict
+
+    def _restore_through_engine(self, state_dict) -> bool:
+        """Mirror of :meth:`_snapshot_state_dict` for third-party state dicts that implement the whole contract: pop the host
+        tensors, restore them with the engine (file -> pinned ring -> device when the backend noted the file, else one H2D;
+        one scatter kernel), insert the device tensors back.  ``BasicTensorAwareStateDict`` does this itself."""
+        from ..basic_state_dict import BasicTensorAwareStateDict
+
+        if isinstance(state_dict, BasicTensorAwareStateDict) or os.environ.get("NVRX_B200_GENERIC_TASD", "1") == "0":
+            return False
+        if not torch.cuda.is_available():
+            return False
+        try:
+            if state_dict.is_hollow:
+                return False
+            host = list(state_dict.pop_tensors())
+        except NotImplementedError:
+            return False
+        if not host or any(t.is_cuda for t in host):
+            state_dict.insert_tensors(host)
+            return False
+        from ...b200 import ptzip
+        from ...b200.engine import SnapshotEngine
+
+        source = getattr(state_dict, "__dict__", {}).pop("_b200_loaded_from", None)
+        file_source = None
+        if source is not None and os.environ.get("NVRX_B200_RESTORE_PREAD", "1") != "0":
+            offs = ptzip.tensor_offsets_in_file(source, host)
+            file_source = (source, offs) if offs is not None else None
+        state_dict.insert_tensors(SnapshotEngine.get().restore(host, file_source=file_source))
+        return True
 
     # ---- save (runs in the writer process) ------------------------------------------------------
     @debug_time("BaseCheckpointManager._save_fn", logger)
@@ -174,8 +205,37 @@ class BaseCheckpointManager(ABC):
 
     # ---- save (trainer side) ----------------------------------------------------------------------
     def _snapshot_state_dict(self, state_dict: TensorAwareStateDict):
-        """Move the payload to the host.  Returns the engine Snapshot, or None when the state dict only offers
-        ``copy_tensors_to_cpu`` (then a device sync is required before the writer may read it)."""
+        """Move the payload to the host.  Returns the engine Snapshot, or None when the state dict made its own
+        (reference-style) host copies, in which case a device sync is required before the writer may read them.
+
+        * ``BasicTensorAwareStateDict`` snapshots through the engine itself.
+        * Any OTHER TensorAwareStateDict that implements the whole contract (``pop_tensors`` / ``insert_tensors``, e.g.
+          Megatron-Core's ``MCoreTensorAwareStateDict``, whose tensors sit inside ShardedTensor objects) gets the same
+          data path through the contract alone: pop the payload, ONE pack + drain, insert the host views back.  That is the
+          round trip ``CliqueReplicationStrategy.replicate`` already relies on (reference ``strategies.py:100-131``).
+        * A state dict that only implements ``copy_tensors_to_cpu`` (the reference's ``SimpleTensorAwareStateDict`` test
+          class raises ``NotImplementedError`` everywhere else) keeps the reference behaviour.
+        ``NVRX_B200_GENERIC_TASD=0`` turns the second case off."""
+        from ..basic_state_dict import BasicTensorAwareStateDict
+
+        if isinstance(state_dict, BasicTensorAwareStateDict):
+            result = state_dict.copy_tensors_to_cpu(non_blocking=True)
+            return result if hasattr(result, "descriptor") else None
+        if os.environ.get("NVRX_B200_GENERIC_TASD", "1") != "0":
+            try:
+                hollow_before = state_dict.is_hollow
+                payload = None if hollow_before else list(state_dict.pop_tensors())
+            except NotImplementedError:
+                payload = None
+            if payload is not None:
+                devices = {t.get_device() for t in payload if t.is_cuda}
+                if len(devices) == 1 and all(t.is_cuda for t in payload):
+                    from ...b200.engine import SnapshotEngine
+
+                    snap = SnapshotEngine.get(devices.pop()).snapshot(payload)
+                    state_dict.insert_tensors(snap.host_views())
+                    return snap
+                state_dict.insert_tensors(payload)  # host or mixed payload: leave it to the state dict
         result = state_dict.copy_tensors_to_cpu(non_blocking=True)
         return result if hasattr(result, "descriptor") else None
 

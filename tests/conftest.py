@@ -20,6 +20,9 @@ os.environ["PYTHONPATH"] = os.pathsep.join([str(PKG_ROOT), str(ROOT), os.environ
 
 GOLDEN = ROOT / "tests" / "golden"
 
+# the reference's own unit tests (verbatim fixtures) are run by tests/test_gpu_reference_suite.py under torchrun, not collected here
+collect_ignore_glob = ["golden/ref_tests/*"]
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

@@ -417,3 +417,51 @@ def test_async_save_of_a_dict_with_host_tensors(monkeypatch, built_library, shm_
                 _same(got, want)
             finally:
                 ckpt.close()
+
+
+def _mcore_like(seed, fake=True):
+    from _mcore_like import MCoreLikeTensorAwareStateDict
+
+    g = torch.Generator().manual_seed(seed)
+    wrap = FakeCudaTensor.wrap if fake else (lambda t: t)
+    model = {f"layers.{i}.w": wrap(torch.randn(33 + i, 17, generator=g)) for i in range(3)}
+    optim = {i: {"exp_avg": wrap(torch.randn(33 + i, 17, generator=g)), "step": wrap(torch.tensor(float(i)))} for i in range(3)}
+    return MCoreLikeTensorAwareStateDict.from_state_dict(model, optim, iteration=seed)
+
+
+def test_mcore_shaped_state_dict_goes_through_the_engine(monkeypatch, built_library, shm_dir, tmp_path, dist_1rank):
+    """Row f4: a third-party TensorAwareStateDict with Megatron-Core's shape (tensors inside ShardedTensor-like objects, a
+    `common` part, its own per-tensor copy methods) is snapshotted and restored by the engine through the ABC contract alone."""
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+    with fake_device(monkeypatch) as (engine, lib):
+        mgr = LocalCheckpointManager(shm_dir / "mc")
+        q = AsyncCallsQueue(persistent=False)
+        try:
+            tasd = _mcore_like(3)
+            want = [plain(t).clone() for t in tasd.tensors]
+            before = len(lib.calls)
+            req = mgr.save(tasd, 5, is_async=True)
+            assert "pack" in lib.calls[before:] and tasd.calls == []  # engine path, not the class's own per-tensor copies
+            assert not tasd.is_hollow and all(not t.is_cuda for t in tasd.tensors)  # host views were inserted back
+            q.schedule_async_request(req)
+            q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+            assert not any(s.busy for s in engine._slots)
+            mgr2 = LocalCheckpointManager(shm_dir / "mc")
+            assert mgr2.find_latest() == 5
+            loaded, cid = mgr2.load()
+            assert loaded.calls == [] and engine.file_restores == 1  # restored by the engine from the file
+            assert loaded.common["iteration"] == 3 and loaded.sharded_state_dict["rerun"].data == {"mode": "disabled"}
+            got = list(loaded.tensors)
+            assert len(got) == len(want) and all(t.is_cuda and torch.equal(plain(t), w) for t, w in zip(got, want))
+            sh = loaded.sharded_state_dict["model"]["layers.1.w"]
+            assert sh.key == "model.layers.1.w" and sh.global_offset == (0, 0) and sh.local_shape == (34, 17)
+            # opt-out keeps the class's own methods (reference behaviour)
+            monkeypatch.setenv("NVRX_B200_GENERIC_TASD", "0")
+            monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)  # the reference path ends in a device sync
+            tasd = _mcore_like(4)
+            mgr.save(tasd, 6, is_async=False)
+            assert tasd.calls == ["copy_tensors_to_cpu"]
+        finally:
+            q.close()

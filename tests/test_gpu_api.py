@@ -269,3 +269,53 @@ def test_many_tensor_finalize_is_fast(shm_dir, dist_1rank, built_library, caplog
     took = [float(r.getMessage().split(" took ")[1].rstrip("s")) for r in caplog.records if "finalize_fn took" in r.getMessage()]
     assert len(took) == 2 and max(took) < 0.1, took
     q.close()
+
+
+def test_mcore_shaped_state_dict_through_the_engine(shm_dir, dist_1rank, built_library):
+    """Row f4: a third-party TensorAwareStateDict shaped like Megatron-Core's MCoreTensorAwareStateDict -- tensors
+    inside ShardedTensor-like objects, a `common` part with a host tensor, its own per-tensor device<->host methods -- takes
+    the engine path through the ABC contract alone (pop -> ONE pack + drain -> insert; restore: file -> ring -> scatter)."""
+    from _mcore_like import MCoreLikeTensorAwareStateDict
+
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    model = {f"layers.{i}.w": torch.randn(257 + i, 129, device="cuda", generator=g) for i in range(6)}
+    optim = {i: {"exp_avg": torch.randn(257 + i, 129, device="cuda", generator=g), "step": torch.tensor(float(i), device="cuda")} for i in range(6)}
+    tasd_ = MCoreLikeTensorAwareStateDict.from_state_dict(model, optim, iteration=9)
+    want = [t.clone() for t in tasd_.tensors]
+    engine = SnapshotEngine.get()
+    launches, restores = engine.launches, engine.file_restores
+    mgr = LocalCheckpointManager(shm_dir / "mcore")
+    q = AsyncCallsQueue(persistent=False)
+    try:
+        req = mgr.save(tasd_, 3, is_async=True)
+        assert tasd_.calls == [] and engine.launches > launches  # the engine packed it; the class's own copy loop did not run
+        for t in model.values():
+            t.zero_()  # training goes on: the snapshot was consistent at save() in stream order
+        q.schedule_async_request(req)
+        q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+        mgr2 = LocalCheckpointManager(shm_dir / "mcore")
+        assert mgr2.find_latest() == 3
+        loaded, cid = mgr2.load()
+        assert cid == (3, 0, "") and loaded.calls == [] and engine.file_restores == restores + 1
+        assert loaded.common["iteration"] == 9 and torch.equal(loaded.common["rng_state"], torch.arange(16, dtype=torch.uint8))
+        got = list(loaded.tensors)
+        assert len(got) == len(want) and all(a.is_cuda and bit_equal(a, b) for a, b in zip(got, want))
+        # and what the reference implementation of the same flow (the class's own methods) stores is the same bytes
+        os.environ["NVRX_B200_GENERIC_TASD"] = "0"
+        try:
+            ref = MCoreLikeTensorAwareStateDict.from_state_dict({k: w.clone() for k, w in zip(model, want[:6])}, {}, iteration=9)
+            mgr3 = LocalCheckpointManager(shm_dir / "mcore_ref")
+            mgr3.save(ref, 1, is_async=False)
+            assert ref.calls == ["copy_tensors_to_cpu"]
+            assert mgr3.find_latest() == 1
+            back, _ = mgr3.load()
+            assert back.calls == ["restore_tensor_device"]
+            assert all(bit_equal(a, b) for a, b in zip(back.tensors, want[:6]))
+        finally:
+            os.environ.pop("NVRX_B200_GENERIC_TASD", None)
+    finally:
+        q.close()
