@@ -226,6 +226,10 @@ int nvrx_hostbuf_readv_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, 
                           int fd, int threads);
 /* crc32 (zlib polynomial) of a payload range computed with `threads` workers and combined. */
 int nvrx_hostbuf_crc32(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int threads, uint32_t* out);
+/* The same for n extents in one call (checksums of all records of a checkpoint container): out[i] = crc32 of
+ * [offsets[i], offsets[i] + nbytes[i]).  The sums use carry-less-multiply folding where the CPU has PCLMULQDQ. */
+int nvrx_hostbuf_crc32v(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, const uint64_t* nbytes, int threads,
+                        uint32_t* out);
 
 /* ---- CRC-32 of packed extents on the GPU ----------------------------------------------------------------------------
  * Replaces the CPU checksum pass of the reference's writer: `torch.save` (async_ckpt/torch_ckpt.py:36-41,

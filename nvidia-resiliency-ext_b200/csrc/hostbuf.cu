@@ -26,6 +26,8 @@
 
 #include "nvrx_snap.h"
 
+extern "C" size_t nvrx_crc32_fold(uint32_t* crc, const uint8_t* p, size_t n);  // crc32_fold.cpp (not part of the ABI)
+
 namespace {
 
 constexpr uint64_t kHeaderBytes = 4096;
@@ -155,6 +157,11 @@ void crc_init() {
 
 uint32_t crc_update(uint32_t crc, const uint8_t* p, uint64_t n) {
     crc = ~crc;
+    {  // carry-less-multiply folding for the bulk (crc32_fold.cpp); the table loop below takes what is left (< 64 B + tail)
+        const size_t took = nvrx_crc32_fold(&crc, p, static_cast<size_t>(n));
+        p += took;
+        n -= took;
+    }
     while (n && (reinterpret_cast<uintptr_t>(p) & 7u)) {
         crc = (crc >> 8) ^ g_tab[0][(crc ^ *p++) & 0xff];
         --n;
@@ -534,6 +541,55 @@ int nvrx_hostbuf_crc32(nvrx_hostbuf* hb, uint64_t offset, uint64_t bytes, int th
     uint32_t crc = crcs[0];
     for (uint64_t t = 1; t < parts; ++t) crc = crc_combine(crc, crcs[t], lens[t]);
     *out = crc;
+    return NVRX_OK;
+}
+
+// crc32 of n extents of the payload at once: pieces of 4 MiB are summed by `threads` workers (across and inside extents) and
+// chained per extent -- one call for the ~1500 records of a checkpoint instead of one thread pool per record.
+int nvrx_hostbuf_crc32v(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets, const uint64_t* nbytes, int threads, uint32_t* out) {
+    if (!hb || n < 0 || (n > 0 && (!offsets || !nbytes || !out))) return NVRX_E_INVALID;
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets[i] > hb->capacity || nbytes[i] > hb->capacity - offsets[i]) return NVRX_E_INVALID;
+    if (n == 0) return NVRX_OK;
+    crc_init();
+    if (threads < 1) threads = 1;
+    const uint8_t* base = hb->map + kHeaderBytes;
+    const uint64_t grain = 4ull << 20;
+    std::vector<uint64_t> first_piece;
+    std::vector<uint32_t> part;
+    try {
+        first_piece.assign(static_cast<size_t>(n) + 1, 0);
+        for (int64_t i = 0; i < n; ++i) first_piece[i + 1] = first_piece[i] + (nbytes[i] + grain - 1) / grain;
+        part.assign(first_piece[n], 0);
+    } catch (const std::bad_alloc&) {
+        return NVRX_E_NOMEM;
+    }
+    const uint64_t total_pieces = first_piece[n];
+    std::atomic<uint64_t> next{0};
+    auto worker = [&] {
+        int64_t ext = 0;
+        while (true) {
+            const uint64_t piece = next.fetch_add(1);
+            if (piece >= total_pieces) break;
+            while (first_piece[ext + 1] <= piece) ++ext;
+            const uint64_t o = (piece - first_piece[ext]) * grain;
+            part[piece] = crc_update(0, base + offsets[ext] + o, std::min<uint64_t>(grain, nbytes[ext] - o));
+        }
+    };
+    const int nthreads = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(threads), std::max<uint64_t>(total_pieces, 1)));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t crc = 0;
+        for (uint64_t pc = first_piece[i]; pc < first_piece[i + 1]; ++pc) {
+            const uint64_t o = (pc - first_piece[i]) * grain;
+            const uint64_t len = std::min<uint64_t>(grain, nbytes[i] - o);
+            crc = (pc == first_piece[i]) ? part[pc] : crc_combine(crc, part[pc], len);
+        }
+        out[i] = crc;
+    }
     return NVRX_OK;
 }
 

@@ -80,6 +80,7 @@ EXPORTED_SYMBOLS = (
     "nvrx_hostbuf_gather",
     "nvrx_hostbuf_readv_fd",
     "nvrx_hostbuf_crc32",
+    "nvrx_hostbuf_crc32v",
     "nvrx_crc_create",
     "nvrx_crc_destroy",
     "nvrx_crc_info",
@@ -170,6 +171,7 @@ def _declare(lib: C.CDLL) -> None:
         "nvrx_hostbuf_gather": (_int, [_vp, _i64, P(_vp), P(_u64), P(_u64), _int]),
         "nvrx_hostbuf_readv_fd": (_int, [_vp, _i64, P(_u64), P(_u64), P(_u64), _int, _int]),
         "nvrx_hostbuf_crc32": (_int, [_vp, _u64, _u64, _int, P(_u32)]),
+        "nvrx_hostbuf_crc32v": (_int, [_vp, _i64, P(_u64), P(_u64), _int, P(_u32)]),
         "nvrx_crc_create": (_int, [_i64, P(_u64), P(_u64), _int, P(_vp)]),
         "nvrx_crc_destroy": (_int, [_vp]),
         "nvrx_crc_info": (_int, [_vp, P(_u64)]),

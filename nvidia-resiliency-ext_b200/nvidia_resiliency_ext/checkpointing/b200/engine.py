@@ -389,6 +389,13 @@ class HostBuffer:
         check(self._lib.nvrx_hostbuf_crc32(self._h, offset, nbytes, threads, C.byref(out)), "nvrx_hostbuf_crc32")
         return out.value
 
+    def crc32v(self, offsets: Sequence[int], nbytes: Sequence[int], threads: int = 16) -> List[int]:
+        """zlib crc32 of every extent ``[offsets[i], +nbytes[i])`` of the payload, one threaded pass."""
+        n = len(offsets)
+        out = (C.c_uint32 * max(n, 1))()
+        check(self._lib.nvrx_hostbuf_crc32v(self._h, n, _u64_array(offsets), _u64_array(nbytes), threads, out), "nvrx_hostbuf_crc32v")
+        return [out[i] for i in range(n)]
+
     def close(self, unlink: Optional[bool] = None) -> None:
         if self._h:
             self._lib.nvrx_hostbuf_destroy(self._h, int(self.owner if unlink is None else unlink))

@@ -21,6 +21,8 @@ from typing import List, Sequence, Tuple
 
 import torch
 
+from .persist import zip_crc_enabled
+
 WRITE_THREADS = int(os.environ.get("NVRX_B200_WRITE_THREADS", "16"))
 
 # (base address, capacity, HostBuffer) ranges the current writer may find tensor storages in
@@ -131,8 +133,8 @@ def _try_link(obj, target: str, records, protocol) -> bool:
     info = getattr(slot, "crc_info", None)
     if info:
         crcs = _gpu_crcs(slot, info, offsets, sizes)
-    elif os.environ.get("NVRX_B200_ZIP_CRC", "0") not in ("", "0"):
-        crcs = [slot.crc32(off, nb, WRITE_THREADS) if nb else 0 for off, nb in zip(offsets, sizes)]
+    elif zip_crc_enabled():
+        crcs = slot.crc32v(offsets, sizes, WRITE_THREADS)
     small = ptzip.small_records(obj, protocol)
     keep = info["ready_offset"] + 8 if info else 0  # the values stay readable in the published file's pad area
     return ptzip.publish_slot("/dev/shm" + slot.name, target, small, offsets, sizes, crcs=crcs, keep_until=keep)
@@ -180,25 +182,41 @@ def save(obj, f, *args, **kwargs) -> str:
     if start != 0 or not isinstance(name, (str, bytes)):
         raise RuntimeError("fastsave.save needs a path or a file object opened on a named file at offset 0")
     reader = torch._C.PyTorchFileReader(os.fspath(name))
-    fd = os.open(name, os.O_RDWR) if is_path else f.fileno()  # read+write: the writer maps the range
+    fd = os.open(name, os.O_RDWR)  # a descriptor of our own, read+write: the writer maps the range, the checksum patch reads
     try:
         by_slot = {}
+        patch, patch_crcs = [], []  # records whose checksum is known here: (name, data offset, size)
+        want_crc = zip_crc_enabled()
         for rec, ptr, nbytes in records:
             if nbytes == 0:
                 continue
             file_off = reader.get_record_offset(rec)
             hb, off = _locate(ptr, nbytes)
             if hb is None:  # a tensor that does not live in a snapshot slot (pass-through host tensor)
-                os.pwrite(fd, C.string_at(ptr, nbytes), file_off)
+                raw = C.string_at(ptr, nbytes)
+                os.pwrite(fd, raw, file_off)
+                if want_crc:
+                    import zlib
+
+                    patch.append((rec, file_off, nbytes))
+                    patch_crcs.append(zlib.crc32(raw))
                 continue
-            ent = by_slot.setdefault(id(hb), (hb, [], [], []))
+            ent = by_slot.setdefault(id(hb), (hb, [], [], [], []))
             ent[1].append(off)
             ent[2].append(nbytes)
             ent[3].append(file_off)
-        for hb, offs, sizes, file_offs in by_slot.values():
+            ent[4].append(rec)
+        for hb, offs, sizes, file_offs, names in by_slot.values():
             hb.writev_fd(offs, sizes, file_offs, fd, WRITE_THREADS)
+            if want_crc:
+                # skip_data left the data records' checksums zero: sum the slot (not the file) with the writer pool and patch
+                patch.extend(zip(names, file_offs, sizes))
+                patch_crcs.extend(hb.crc32v(offs, sizes, WRITE_THREADS))
+        if patch:
+            from . import ptzip
+
+            ptzip.patch_record_crcs(fd, patch, patch_crcs)
     finally:
         del reader
-        if is_path:
-            os.close(fd)
+        os.close(fd)
     return "parallel"

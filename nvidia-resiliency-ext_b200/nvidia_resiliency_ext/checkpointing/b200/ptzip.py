@@ -428,6 +428,48 @@ def tensor_offsets_in_file(path, tensors: Sequence[torch.Tensor]) -> Optional[Li
     return offs
 
 
+def patch_record_crcs(fd: int, records: Sequence[Tuple[str, int, int]], crcs: Sequence[int]) -> int:
+    """Write the crc32 of data records into a container PyTorch laid out with ``torch.serialization.skip_data()`` (it leaves
+    them zero: the data was not there to be summed).  ``records`` = ``(record name as the reader reports it, e.g. "data/7",
+    data offset, size)``.  PyTorch's writer sets general-purpose flag bit 3, so a record's checksum lives in the data descriptor
+    behind its data (signature 50 4b 07 08, then the crc) and in its central-directory entry; both are patched, the local header stays zero as
+    PyTorch writes it.  Returns the number of records patched.  With this the file verifies (``zipfile.ZipFile.testzip()``)
+    exactly like a file the reference's ``torch.save`` wrote (``async_ckpt/torch_ckpt.py:36-41``)."""
+    want = {}
+    for (name, off, size), crc in zip(records, crcs):
+        want[name] = crc & _U32
+        if os.pread(fd, 4, off + size) == b"PK\x07\x08":
+            os.pwrite(fd, struct.pack("<I", crc & _U32), off + size + 4)
+    end = os.fstat(fd).st_size
+    tail_len = min(end, 65536 + 22 + 76)
+    tail = os.pread(fd, tail_len, end - tail_len)
+    eocd = tail.rfind(b"PK\x05\x06")
+    if eocd < 0:
+        raise ValueError("not a zip container: end-of-central-directory record not found")
+    cd_size, cd_off = struct.unpack_from("<II", tail, eocd + 12)
+    if cd_off == 0xFFFFFFFF or cd_size == 0xFFFFFFFF:
+        loc = tail.rfind(b"PK\x06\x07", 0, eocd)
+        if loc < 0:
+            raise ValueError("zip64 locator missing")
+        (z64_off,) = struct.unpack_from("<Q", tail, loc + 8)
+        z64 = os.pread(fd, 56, z64_off)
+        if z64[:4] != b"PK\x06\x06":
+            raise ValueError("zip64 end-of-central-directory record missing")
+        cd_size, cd_off = struct.unpack_from("<QQ", z64, 40)
+    cd = bytearray(os.pread(fd, cd_size, cd_off))
+    pos, patched = 0, 0
+    while pos + 46 <= len(cd) and cd[pos:pos + 4] == b"PK\x01\x02":
+        name_len, extra_len, comment_len = struct.unpack_from("<HHH", cd, pos + 28)
+        name = bytes(cd[pos + 46:pos + 46 + name_len]).decode("utf-8", "replace")
+        key = name.split("/", 1)[1] if "/" in name else name  # "<archive>/data/7" -> "data/7"
+        if key in want:
+            struct.pack_into("<I", cd, pos + 16, want[key])
+            patched += 1
+        pos += 46 + name_len + extra_len + comment_len
+    os.pwrite(fd, bytes(cd), cd_off)
+    return patched
+
+
 def record_crcs(path, n_storages: int) -> Optional[List[int]]:
     """CRC-32 fields of the records ``data/0 .. data/n-1`` of a checkpoint file (from its central directory), or None when the
     file is not such an archive.  A zero field on a non-empty record means "written without checksums" (our fast writers'

@@ -228,6 +228,8 @@ def test_default_paths_torch_async_and_local_manager(monkeypatch, built_library,
                 ckpt.finalize_async_save(blocking=True)
                 assert os.stat(path).st_nlink == 1  # a copy, not a link
                 _same(torch.load(path, weights_only=False), _state(i, wrap=False))
+                with zipfile.ZipFile(path) as z:  # default mode: every record carries its checksum, like a torch.save file
+                    assert z.testzip() is None and all(zi.CRC for zi in z.infolist() if "/data/" in zi.filename and zi.file_size)
             assert len(engine._slots) == 2 and not any(s.busy for s in engine._slots)
         finally:
             ckpt.close()
@@ -247,6 +249,8 @@ def test_default_paths_torch_async_and_local_manager(monkeypatch, built_library,
 
             time.sleep(0.5)  # cleanup of iteration 1 runs in a background thread
             assert sorted(p.name for p in mgr.local_ckpt_dir.iterdir()) == ["iter_0000002_0_local.pt"]
+            with zipfile.ZipFile(mgr.local_ckpt_dir / "iter_0000002_0_local.pt") as z:
+                assert z.testzip() is None
             assert mgr.find_latest() == 2
             loaded, _ = mgr.load()
             _same(loaded.state_dict, _state(22, wrap=False))
@@ -410,6 +414,8 @@ def test_async_save_of_a_dict_with_host_tensors(monkeypatch, built_library, shm_
                 path = shm_dir / f"mixed{int(persistent)}.pt"
                 ckpt.async_save(sd, path)
                 ckpt.finalize_async_save(blocking=True)
+                with zipfile.ZipFile(path) as z:
+                    assert z.testzip() is None  # slot records and the pass-through host tensors alike
                 got = torch.load(path, weights_only=False)
                 assert torch.equal(got["rng_state"], want["rng_state"]) and got["extra"]["cpu_list"][1:] == [3.5, "text"]
                 assert torch.equal(got["extra"]["cpu_list"][0], torch.arange(7))

@@ -97,6 +97,10 @@ def test_parallel_writer_produces_a_plain_torch_checkpoint(built_library, tmp_pa
         else:
             how = fastsave.save(obj, path)
     assert how == "parallel"
+    import zipfile
+
+    with zipfile.ZipFile(path) as z:
+        assert z.testzip() is None  # record checksums are on by default
     torch.save(obj, tmp_path / "stock.pt")
     fast, stock = torch.load(path), torch.load(tmp_path / "stock.pt")
     for a, b in zip(fast["slot"], stock["slot"]):
@@ -254,5 +258,37 @@ def test_writev_fd_with_preallocation(built_library, tmp_path, monkeypatch):
             finally:
                 os.close(fd)
                 os.unlink(path)
+    finally:
+        hb.close()
+
+
+def test_crc32_fold_and_batched_sums_match_zlib(built_library):
+    """The carry-less-multiply CRC (csrc/crc32_fold.cpp) behind nvrx_hostbuf_crc32 / crc32v against zlib: every alignment,
+    lengths around the 16 / 64-byte folding blocks and the 4 MiB piece boundary of the batched call."""
+    import os
+    import random
+    import zlib
+
+    import numpy as np
+
+    from nvidia_resiliency_ext.checkpointing.b200.engine import HostBuffer
+
+    n = 24 << 20
+    hb = HostBuffer.create(n, name=f"/nvrx_crc_t_{os.getpid()}", pin=False, prefault_threads=2)
+    try:
+        arr = np.frombuffer((__import__("ctypes").c_uint8 * n).from_address(hb.data_ptr), dtype=np.uint8)
+        arr[:] = np.random.default_rng(3).integers(0, 256, n, dtype=np.uint8)
+        rnd = random.Random(5)
+        lens = [0, 1, 15, 16, 17, 63, 64, 65, 79, 80, 127, 128, 129, 1000, 4095, 4096, 4097, (4 << 20) - 1, 4 << 20, (4 << 20) + 1, (9 << 20) + 7]
+        offs, sizes = [], []
+        for ln in lens * 3:
+            off = rnd.randrange(0, n - ln)
+            offs.append(off)
+            sizes.append(ln)
+            assert hb.crc32(off, ln, threads=1) == zlib.crc32(arr[off : off + ln].tobytes())
+        for threads in (1, 5):
+            got = hb.crc32v(offs, sizes, threads=threads)
+            assert got == [zlib.crc32(arr[o : o + s].tobytes()) for o, s in zip(offs, sizes)]
+        assert hb.crc32(0, n, threads=4) == zlib.crc32(arr.tobytes())
     finally:
         hb.close()

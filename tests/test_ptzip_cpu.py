@@ -108,3 +108,54 @@ def test_payload_can_be_written_before_the_container(built_library, tmp_path):
             ptzip.write_container(fd, layout, small, file_size=layout.end + 10)
         finally:
             os.close(fd)
+
+
+def test_patch_record_crcs_also_in_zip64_containers(tmp_path):
+    """ptzip.patch_record_crcs on a container PyTorch laid out with skip_data: data descriptors and central directory take
+    the checksums (small file: zipfile.testzip passes afterwards; > 4 GiB sparse file: the zip64 directory is found and patched)."""
+    import os
+    import zipfile
+    import zlib
+
+    import torch
+
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+
+    sd = {"a": torch.arange(1000, dtype=torch.float32), "b": {"c": torch.ones(33, dtype=torch.int64)}, "z": torch.empty(0)}
+    path = tmp_path / "small.pt"
+    with torch.serialization.skip_data():
+        torch.save(sd, path)
+    reader = torch._C.PyTorchFileReader(str(path))
+    recs, crcs = [], []
+    fd = os.open(path, os.O_RDWR)
+    try:
+        for name, t in (("data/0", sd["a"]), ("data/1", sd["b"]["c"])):
+            raw = t.numpy().tobytes()
+            off = reader.get_record_offset(name)
+            os.pwrite(fd, raw, off)
+            recs.append((name, off, len(raw)))
+            crcs.append(zlib.crc32(raw))
+        assert ptzip.patch_record_crcs(fd, recs, crcs) == 2
+    finally:
+        os.close(fd)
+    with zipfile.ZipFile(path) as z:
+        assert z.testzip() is None
+    got = torch.load(path)
+    assert torch.equal(got["a"], sd["a"]) and torch.equal(got["b"]["c"], sd["b"]["c"])
+
+    big = {"big": torch.empty(4 * 1024**3 + 4096, dtype=torch.uint8), "tail": torch.empty(1 << 20, dtype=torch.uint8)}  # never touched
+    path = tmp_path / "big.pt"
+    with torch.serialization.skip_data():
+        torch.save(big, path)
+    reader = torch._C.PyTorchFileReader(str(path))
+    recs = [(n, reader.get_record_offset(n), big[k].numel()) for n, k in (("data/0", "big"), ("data/1", "tail"))]
+    assert recs[1][1] > 4 * 1024**3
+    fd = os.open(path, os.O_RDWR)
+    try:
+        assert ptzip.patch_record_crcs(fd, recs, [0x11223344, 0x55667788]) == 2
+    finally:
+        os.close(fd)
+    with zipfile.ZipFile(path) as z:
+        by_name = {zi.filename.split("/", 1)[1]: zi for zi in z.infolist()}
+        assert by_name["data/0"].CRC == 0x11223344 and by_name["data/1"].CRC == 0x55667788
+        assert by_name["data/1"].header_offset > 4 * 1024**3
