@@ -531,8 +531,6 @@ def run_arm(args, rank, world, local):
         del loop
     arm.close()
     shutil.rmtree(out_dir, ignore_errors=True)
-    if engine_arm:
-        engine.trim()  # give the async slots back before the local-manager leg pins its own
     local_leg = {} if args.no_restore else local_manager_leg(args.impl, sd, tensors, total, rank, args.narrow)
     ceiling = None if args.no_ceiling else d2h_ceiling(dev, world)
     if engine_arm:

@@ -193,12 +193,12 @@ def _geometry(group, all_placeholders, align: int, world: int, container: bool =
 
 
 def _container_exchange(engine: SnapshotEngine, group, world: int) -> bool:
-    """Zero-copy persistence for replicated saves (opt-in with ``NVRX_B200_ZERO_COPY=1``, which has to be set on every
+    """Zero-copy persistence for replicated saves (opt-in with ``NVRX_B200_ZERO_COPY_REPLICAS=1``, which has to be set on every
     member): possible while the pool of EVERY member can hold one slot per clique member for this save -- the geometry of a
     member's slice is computed by all of them, so the decision is a vote (one small tensor collective, only in this mode)."""
-    from .fastsave import zero_copy_enabled
+    from .fastsave import replicated_zero_copy_enabled
 
-    if not zero_copy_enabled():
+    if not replicated_zero_copy_enabled():
         return False
     return all(group.all_gather_int(int(engine._spare_slots() >= world)))
 

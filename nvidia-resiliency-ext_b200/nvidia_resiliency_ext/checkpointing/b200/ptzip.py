@@ -156,13 +156,21 @@ def _crc_of_file_range(fd: int, off: int, n: int) -> int:
 
 
 def small_records(obj: Any, protocol: int = torch.serialization.DEFAULT_PROTOCOL) -> List[Tuple[str, bytes]]:
-    """Everything PyTorch writes for ``obj`` besides tensor data (``data.pkl``, ``byteorder``, ``version``, ...)."""
-    buf = io.BytesIO()
-    with torch.serialization.skip_data():
-        torch.save(obj, buf, pickle_protocol=protocol)
-    buf.seek(0)
-    reader = torch._C.PyTorchFileReader(buf)
-    return [(n, bytes(reader.get_record(n))) for n in reader.get_all_records() if not n.startswith("data/")]
+    """Everything PyTorch writes for ``obj`` besides tensor data (``data.pkl``, ``byteorder``, ``version``, ...).
+
+    PyTorch itself produces them: ``torch.save`` with the data skipped into a scratch FILE, which the writer leaves sparse
+    (it seeks over the records).  An in-memory ``BytesIO`` target must not be used here: seeking over 16 GB of skipped records
+    and then writing makes it allocate and zero all of it (8 s per checkpoint, measured on the B200 box in round 2)."""
+    import tempfile
+
+    scratch_dir = "/dev/shm" if os.access("/dev/shm", os.W_OK) else None
+    with tempfile.NamedTemporaryFile(dir=scratch_dir, prefix="nvrx_b200_skel_", suffix=".pt") as tf:
+        with torch.serialization.skip_data():
+            torch.save(obj, tf.name, pickle_protocol=protocol)
+        reader = torch._C.PyTorchFileReader(tf.name)
+        out = [(n, bytes(reader.get_record(n))) for n in reader.get_all_records() if not n.startswith("data/")]
+        del reader
+    return out
 
 
 def tail_size(archive: str, small: Sequence[Tuple[str, bytes]], n_storages: int, force_zip64: bool = False) -> int:

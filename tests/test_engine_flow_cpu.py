@@ -210,15 +210,21 @@ def test_dcp_writer_cuda_branch(monkeypatch, built_library, tmp_path, dist_1rank
 
 @pytest.mark.parametrize("persistent", [True, False])
 def test_default_paths_torch_async_and_local_manager(monkeypatch, built_library, shm_dir, tmp_path, dist_1rank, persistent):
-    """No switches set: the copying writer, slot release on finalize, cleanup of older iterations, gather-based restore."""
+    """NVRX_B200_ZERO_COPY=0 (the default is the hard-link publish): the copying writer, slot release on finalize, cleanup of
+    older iterations, restore from the file."""
     from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
     from nvidia_resiliency_ext.checkpointing.async_ckpt.torch_ckpt import TorchAsyncCheckpoint
     from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
     from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
     from nvidia_resiliency_ext.checkpointing.utils import preload_tensors
 
-    for var in ("NVRX_B200_ZERO_COPY", "NVRX_B200_GPU_CRC", "NVRX_B200_VERIFY_RESTORE", "NVRX_B200_RESTORE_PREAD"):
+    for var in ("NVRX_B200_GPU_CRC", "NVRX_B200_VERIFY_RESTORE", "NVRX_B200_RESTORE_PREAD"):
         monkeypatch.delenv(var, raising=False)
+    from nvidia_resiliency_ext.checkpointing.b200 import fastsave
+
+    monkeypatch.delenv("NVRX_B200_ZERO_COPY", raising=False)
+    assert fastsave.zero_copy_enabled() and not fastsave.replicated_zero_copy_enabled()  # the defaults
+    monkeypatch.setenv("NVRX_B200_ZERO_COPY", "0")
     with fake_device(monkeypatch) as (engine, lib):
         ckpt = TorchAsyncCheckpoint(persistent_queue=persistent)
         try:

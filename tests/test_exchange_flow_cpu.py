@@ -245,6 +245,7 @@ def test_container_landing_publishes_as_a_checkpoint(fake, monkeypatch, shm_dir)
 
     engine, xch = fake
     monkeypatch.setenv("NVRX_B200_ZERO_COPY", "1")
+    monkeypatch.setenv("NVRX_B200_ZERO_COPY_REPLICAS", "1")
     tensors = _tensors()
     group = _Group()
     assert xch._container_exchange(engine, group, 1)

@@ -143,6 +143,7 @@ def test_replicated_save_retrieve_restore_pairs(built_library, shm_dir):
 def _w_replicated_zero_copy(rank, world, root, jump, factor, kill):
     import os
 
+    os.environ["NVRX_B200_ZERO_COPY_REPLICAS"] = "1"
     os.environ["NVRX_B200_ZERO_COPY"] = "1"  # on every member: the container geometry of a slice is computed by all of them
     _w_replicated_save_and_restore(rank, world, root, jump, factor, kill)
     # every surviving file on this rank is a hard link to one of its pinned slots, not a copy

@@ -222,12 +222,17 @@ def test_lost_everywhere_is_not_latest(tmp_path):
     run_ranks(_w_no_replica_left, 2, str(tmp_path))
 
 
-def test_saving_does_not_switch_off_the_trainers_zip_checksums(tmp_path, dist_1rank, built_library):
-    """The fast writer skips zip CRCs while it saves a snapshot; that is a process-wide PyTorch switch and a synchronous
-    save runs in the trainer, so it has to be back to its previous value afterwards."""
+def test_saving_does_not_switch_off_the_trainers_zip_checksums(tmp_path, dist_1rank, built_library, monkeypatch):
+    """Checksums are on by default (nothing is switched).  With NVRX_B200_ZIP_CRC=0 the writer skips zip CRCs while it saves a
+    snapshot; that is a process-wide PyTorch switch and a synchronous save runs in the trainer, so it has to be back to its
+    previous value afterwards."""
     from nvidia_resiliency_ext.checkpointing.b200.persist import fast_zip_writes
 
     assert torch.serialization.get_crc32_options() is True
+    monkeypatch.delenv("NVRX_B200_ZIP_CRC", raising=False)
+    with fast_zip_writes():
+        assert torch.serialization.get_crc32_options() is True
+    monkeypatch.setenv("NVRX_B200_ZIP_CRC", "0")
     with fast_zip_writes():
         assert torch.serialization.get_crc32_options() is False
     assert torch.serialization.get_crc32_options() is True

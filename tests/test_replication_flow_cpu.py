@@ -31,6 +31,7 @@ def _worker(rank, world, root, mode, zero_copy, kill):
     os.environ["NVRX_B200_STREAM_CHUNK_MB"] = "0"  # 512-byte chunks: many ring turns
     if zero_copy:
         os.environ["NVRX_B200_ZERO_COPY"] = "1"
+        os.environ["NVRX_B200_ZERO_COPY_REPLICAS"] = "1"
     mp = pytest.MonkeyPatch()
     try:
         with fake_device(mp) as (engine, lib):

@@ -83,12 +83,12 @@ if [[ $WHAT == sanitize ]]; then
 fi
 if [[ $WHAT == ncu_list ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk_ -c 40 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 10 --warmup 3 --e2e-steps 2 --e2e-warmup 1 --no-cpu-baseline --no-verify > gpurun_out/bench_under_ncu.log 2>&1
+      python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify --no-restore --no-training-loop --no-ceiling > gpurun_out/bench_under_ncu.log 2>&1
   grep -c walk_ gpurun_out/launches.csv
 fi
 if [[ $WHAT == all || $WHAT == ncu ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk_ -c 40 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 10 --warmup 3 --e2e-steps 2 --e2e-warmup 1 --no-cpu-baseline --no-verify > gpurun_out/bench_under_ncu.log 2>&1
+      python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify --no-restore --no-training-loop --no-ceiling > gpurun_out/bench_under_ncu.log 2>&1
   grep -c walk_ gpurun_out/launches.csv
   NCU_REPS=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:walk_ -c 6 -f -o gpurun_out/prof_walk \
       python tools/ncu_target.py > gpurun_out/ncu_full.log 2>&1
