@@ -385,13 +385,21 @@ int nvrx_hostbuf_writev_fd(nvrx_hostbuf* hb, int64_t n, const uint64_t* offsets,
     }
     const uint64_t map_lo = lo & ~uint64_t(4095);
     uint8_t* mapped = nullptr;
-    if (getenv("NVRX_B200_WRITE_FALLOCATE")) {
-        // opt-in (to be measured on the target box): let the kernel allocate the destination pages in one call instead of one
-        // page fault per 4 KiB from 16 threads -- on tmpfs the faults, not the copy, bound a write into a fresh file.
-        // Best effort: file systems without fallocate support just fault in as before.
-        (void)posix_fallocate(fd, static_cast<off_t>(map_lo), static_cast<off_t>(hi - map_lo));
+    bool may_map = !getenv("NVRX_B200_WRITE_PWRITE");
+    if (!getenv("NVRX_B200_NO_FALLOCATE")) {
+        // Allocate the destination range up front.  (1) A store into a mapping of a sparse file that the file system cannot
+        // back (ENOSPC on the local SSD, tmpfs size limit, cgroup memory limit) is a SIGBUS that kills the writer with no
+        // message; posix_fallocate reports the same condition as an errno.  (2) One in-kernel allocation pass is cheaper than
+        // one page fault per 4 KiB from 16 threads (16 GB into a fresh /dev/shm file: 4.9 s instead of 6.4 s on the B200 box).
+        const int rc = posix_fallocate(fd, static_cast<off_t>(map_lo), static_cast<off_t>(hi - map_lo));
+        if (rc == EOPNOTSUPP || rc == EINVAL || rc == ENOSYS) {
+            may_map = false;  // cannot pre-allocate here: use pwrite, whose errors are errnos as well
+        } else if (rc != 0) {
+            errno = rc;
+            return NVRX_E_SYS;
+        }
     }
-    if (!getenv("NVRX_B200_WRITE_PWRITE")) {
+    if (may_map) {
         void* m = mmap(nullptr, hi - map_lo, PROT_READ | PROT_WRITE, MAP_SHARED, fd, static_cast<off_t>(map_lo));
         if (m != MAP_FAILED) mapped = static_cast<uint8_t*>(m);
     }

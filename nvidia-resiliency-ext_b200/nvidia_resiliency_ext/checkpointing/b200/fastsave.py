@@ -184,13 +184,16 @@ def save(obj, f, *args, **kwargs) -> str:
 
             ptzip.save(obj, named, locate=_locate_or_none, threads=WRITE_THREADS, crcs=_gpu_crcs(slot, info, offsets, sizes))
             return "parallel+gpu-crc"
+    name = named
+    if start != 0 or not isinstance(name, str) or (not is_path and not os.path.exists(name)):
+        # an unnamed file object (BytesIO, pipe) or a write that does not start the file: nothing the parallel writer can fill
+        # in by offset -- the stock writer handles those (checked BEFORE anything is emitted into f)
+        torch.save(obj, f, **kwargs)
+        return "torch"
     with torch.serialization.skip_data():
         torch.save(obj, f, **kwargs)
     if not is_path:
         f.flush()
-    name = os.fspath(f) if is_path else getattr(f, "name", None)
-    if start != 0 or not isinstance(name, (str, bytes)):
-        raise RuntimeError("fastsave.save needs a path or a file object opened on a named file at offset 0")
     reader = torch._C.PyTorchFileReader(os.fspath(name))
     fd = os.open(name, os.O_RDWR)  # a descriptor of our own, read+write: the writer maps the range, the checksum patch reads
     try:

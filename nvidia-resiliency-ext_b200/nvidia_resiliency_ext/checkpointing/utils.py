@@ -108,6 +108,9 @@ def preload_tensors(state_dict: Dict, non_blocking=True, *, narrow: bool = False
     ``non_blocking=False`` waits for the drain (event wait, not a device-wide sync) before returning.
     ``narrow=True``        (new, opt-in) fp32 tensors are stored as bf16 (round-to-nearest-even).
 
+    Lifetime: the returned tensors are views of a pooled pinned slot.  With ``return_snapshot=True`` the caller owns the
+    handle (``snapshot.release()`` when done); otherwise the slot is released when the last returned tensor is collected.
+
     State dicts without CUDA tensors are returned as an out-of-place copy of the structure without touching
     the engine (this is the reference's CPU-only case, BASELINE config C1).
     """
@@ -123,11 +126,33 @@ def preload_tensors(state_dict: Dict, non_blocking=True, *, narrow: bool = False
     if len(devices) != 1:
         raise ValueError(f"preload_tensors: tensors live on several CUDA devices {sorted(devices)}")
     snap = SnapshotEngine.get(devices.pop()).snapshot(tensors, narrow=narrow)
-    views = iter(snap.host_views())
+    host = snap.host_views()
+    if not return_snapshot:
+        # nobody else holds the Snapshot: the pinned slot stays reserved exactly as long as one of the returned views is alive
+        # (the reference hands out tensors the caller owns; here they are windows into a pooled slot, which must neither be
+        # reused under them nor stay reserved after them)
+        keepalive = _ReleaseWithLastView(snap)
+        for v in host:
+            if isinstance(v, torch.Tensor) and not v.is_cuda:
+                v._nvrx_slot_keepalive = keepalive
+    views = iter(host)
     out = dict_list_map_outplace(lambda v: next(views) if isinstance(v, torch.Tensor) else v, state_dict)
     if not non_blocking:
         snap.wait()
     return (out, snap) if return_snapshot else out
+
+
+class _ReleaseWithLastView:
+    """Referenced by every host view of a snapshot; releases the snapshot's slot when the last of them is collected."""
+
+    def __init__(self, snap):
+        self._snap = snap
+
+    def __del__(self):
+        try:
+            self._snap.release()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
 
 @contextmanager

@@ -477,3 +477,28 @@ def test_mcore_shaped_state_dict_goes_through_the_engine(monkeypatch, built_libr
             assert tasd.calls == ["copy_tensors_to_cpu"]
         finally:
             q.close()
+
+
+def test_preload_tensors_views_keep_their_slot_and_give_it_back(monkeypatch, built_library, dist_1rank):
+    """preload_tensors() without return_snapshot hands out views of a pooled slot and no handle -- the slot must stay
+    reserved while a view is alive and come back afterwards (it used to stay busy for good)."""
+    import gc
+
+    from nvidia_resiliency_ext.checkpointing.utils import preload_tensors
+
+    with fake_device(monkeypatch) as (engine, lib):
+        kept = []
+        for i in range(6):  # more calls than the pool has slots
+            host = preload_tensors(_state(i), non_blocking=False)
+            _same(host, _state(i, wrap=False))
+            busy = [s for s in engine._slots if s.busy]
+            assert len(busy) == 1 + len(kept)
+            if i == 0:
+                kept.append(host)  # one result stays alive: its slot must not be handed out again
+            del host
+            gc.collect()
+            assert sum(s.busy for s in engine._slots) == len(kept)
+        _same(kept[0], _state(0, wrap=False))  # still intact after five more snapshots
+        kept.clear()
+        gc.collect()
+        assert not any(s.busy for s in engine._slots)

@@ -292,3 +292,53 @@ def test_crc32_fold_and_batched_sums_match_zlib(built_library):
         assert hb.crc32(0, n, threads=4) == zlib.crc32(arr.tobytes())
     finally:
         hb.close()
+
+
+def test_fastsave_falls_back_before_writing_into_unnamed_targets(built_library, tmp_path):
+    """a BytesIO / offset target must get a complete stock torch.save, not a payload-less container followed by an
+    exception."""
+    import io
+
+    from nvidia_resiliency_ext.checkpointing.b200 import fastsave
+
+    hb = make_hb(1 << 20)
+    v = hb.segment(0, 4000, torch.float32, (1000,))
+    v.copy_(torch.arange(1000.0))
+    obj = {"v": v, "k": 1}
+    with fastsave.slot_ranges([(hb.data_ptr, hb.capacity, hb)]):
+        buf = io.BytesIO()
+        assert fastsave.save(obj, buf) == "torch"
+        buf.seek(0)
+        assert torch.equal(torch.load(buf)["v"], torch.arange(1000.0))
+        with open(tmp_path / "off.bin", "w+b") as fh:
+            fh.write(b"x" * 100)
+            assert fastsave.save(obj, fh) == "torch"
+            fh.seek(100)
+            assert torch.equal(torch.load(io.BytesIO(fh.read()))["v"], torch.arange(1000.0))
+    del v
+    hb.close()
+
+
+def test_writer_reports_a_full_file_system_as_an_error(built_library, tmp_path):
+    """the destination range is allocated before it is mapped, so "no space" is an errno (NVRX_E_SYS), not a SIGBUS
+    in the writer process.  A file limit (RLIMIT_FSIZE) stands in for the full disk."""
+    import resource
+    import signal
+
+    from nvidia_resiliency_ext.checkpointing.b200._cabi import SnapError
+
+    hb = make_hb(8 << 20)
+    path = tmp_path / "limited.bin"
+    old = resource.getrlimit(resource.RLIMIT_FSIZE)
+    old_handler = signal.signal(signal.SIGXFSZ, signal.SIG_IGN)
+    fd = os.open(path, os.O_CREAT | os.O_RDWR, 0o644)
+    try:
+        resource.setrlimit(resource.RLIMIT_FSIZE, (1 << 20, old[1]))
+        with pytest.raises(SnapError) as exc:
+            hb.writev_fd([0], [8 << 20], [0], fd, threads=2)
+        assert exc.value.status == 1003  # NVRX_E_SYS with errno EFBIG
+    finally:
+        resource.setrlimit(resource.RLIMIT_FSIZE, old)
+        signal.signal(signal.SIGXFSZ, old_handler)
+        os.close(fd)
+        hb.close()
