@@ -404,8 +404,13 @@ def local_manager_leg(arm_name, sd, tensors, total, rank, narrow):
             from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
             from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
 
+            from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
+
             mgr = LocalCheckpointManager(root, session_id=f"r{rank}")
             q = AsyncCallsQueue(persistent=False)
+            # like TorchAsyncCheckpoint.warmup(): staging and host slot for THIS state exist before the timed save (the async
+            # loop above may have run on narrowed, i.e. smaller, snapshots; the reference arm's pinned cache is warm from its loop)
+            SnapshotEngine.get().reserve(sum(t.numel() * t.element_size() for t in tensors) + (len(tensors) + 8) * 1024)
             tasd = BasicTensorAwareStateDict(fresh_containers(sd))
             torch.cuda.synchronize()
             dist.barrier()

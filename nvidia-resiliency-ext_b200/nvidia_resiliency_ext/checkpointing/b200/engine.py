@@ -946,10 +946,21 @@ class SnapshotEngine:
                 assert o.is_cuda and o.is_contiguous() and o.dtype == td and o.shape == t.shape
         if resident is None and file_source is not None and not (expect_crcs is not None and any(expect_crcs)):
             return self._restore_from_file(out, mask, file_source)
+        keep_busy = False
+        if resident is None and file_source is None:
+            # Host tensors that ARE views of one of this engine's pinned slots (a state dict that was just saved: after
+            # ``save()`` its tensors are windows into the snapshot slot, and the reference's tests restore exactly such an
+            # object, tests/checkpointing/unit/test_basic_local.py:62-64) are restored from where they lie.  Gathering them into
+            # "a free slot" could pick the very slot they live in and overwrite them while they are being read.
+            held = self._slot_holding(host_tensors)
+            if held is not None and held[1] is None:
+                host_tensors = [t.clone() for t in host_tensors]  # views of a slot in no usable order: take them out first
+            elif held is not None:
+                resident, keep_busy = held, held[0].busy
         if resident is not None:
             slot, offsets = resident
             plan = self._plan_for(out, mask, offsets=list(offsets))
-            assert plan.staging_bytes <= slot.buf.capacity and not slot.busy
+            assert plan.staging_bytes <= slot.buf.capacity and (keep_busy or not slot.busy)
             slot.busy = True  # nobody may pick it while the H2D reads it (it is also protected by its link count)
             self.resident_restores += 1
         else:
@@ -1005,8 +1016,36 @@ class SnapshotEngine:
                         f"file says {expect_crcs[bad[0]]:#010x}) -- the checkpoint is corrupt",
                     )
         finally:
-            self._release(slot)
+            if not keep_busy:
+                self._release(slot)
         return out
+
+    def _slot_holding(self, host_tensors: Sequence[torch.Tensor]):
+        """``(slot, payload offsets)`` when every non-empty tensor is a contiguous view into ONE slot of this engine, ascending
+        and 16-byte aligned (a plan can read them in place); ``(slot, None)`` when they touch a slot in any other way; None
+        when they have nothing to do with the slots."""
+        live = [t for t in host_tensors if t.numel()]
+        if not live:
+            return None
+        for slot in self._slots:
+            if slot.buf is None:
+                continue
+            base, cap = slot.buf.data_ptr, slot.buf.capacity
+            inside = [base <= t.data_ptr() < base + cap for t in live]
+            if not any(inside):
+                continue
+            if not all(inside):
+                return slot, None
+            offs, end = [], 0
+            for t in host_tensors:
+                nb = t.numel() * t.element_size()
+                off = (t.data_ptr() - base) if nb else -(-end // 16) * 16
+                if nb and (off < end or off % 16 or off + nb > cap or not t.is_contiguous()):
+                    return slot, None
+                offs.append(off)
+                end = off + nb
+            return slot, offs
+        return None
 
     RESTORE_CHUNK = int(os.environ.get("NVRX_B200_RESTORE_CHUNK_MB", "64")) << 20
     RESTORE_RING = int(os.environ.get("NVRX_B200_RESTORE_RING", "4"))

@@ -16,4 +16,8 @@ if __name__ == "__main__":
     DST.mkdir(parents=True, exist_ok=True)
     for name in FILES:
         shutil.copyfile(SRC / name, DST / name)
+    # test_async_writer.py imports `tests.checkpointing.unit` absolutely; an unrelated regular package called `tests` in
+    # site-packages would shadow a namespace package here, so the two directories above `unit` become regular packages
+    for pkg in (DST.parent, DST.parent.parent):
+        (pkg / "__init__.py").touch()
     print(f"copied {len(FILES)} files to {DST}")

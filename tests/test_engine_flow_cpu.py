@@ -502,3 +502,32 @@ def test_preload_tensors_views_keep_their_slot_and_give_it_back(monkeypatch, bui
         kept.clear()
         gc.collect()
         assert not any(s.busy for s in engine._slots)
+
+
+@pytest.mark.parametrize("zero_copy", ["1", "0"])
+def test_restoring_the_state_dict_that_was_just_saved(monkeypatch, built_library, tmp_path, dist_1rank, zero_copy):
+    """Reference test_basic_local.py:62-64: after save() the caller's state dict holds host tensors -- here views of the
+    snapshot slot, which is free again once the save is finalized -- and ``restore_tensor_device()`` on it must give the
+    original values back.  With the container geometry of the default mode the views do not sit at the dense offsets of a
+    restore plan; gathering them into "a free slot" picked the slot they live in (found on the B200 box in round 2)."""
+    from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+    monkeypatch.setenv("NVRX_B200_ZERO_COPY", zero_copy)
+    with fake_device(monkeypatch) as (engine, lib):
+        mgr = LocalCheckpointManager(tmp_path / "disk")  # not /dev/shm: the slot is released, not published
+        sd = BasicTensorAwareStateDict(_state(8))
+        mgr.save(sd, 1, is_async=False)
+        assert not any(s.busy for s in engine._slots) and all(not t.is_cuda for t in sd.tensors)
+        before = engine.resident_restores
+        sd.restore_tensor_device()
+        assert engine.resident_restores == before + 1 and not any(s.busy for s in engine._slots)
+        _same(sd.state_dict, _state(8, wrap=False))
+        # scrambled views of a slot (not ascending) are taken out of the slot before anything is gathered
+        host = BasicTensorAwareStateDict(_state(9))
+        snap = host.copy_tensors_to_cpu(non_blocking=False)
+        views = list(host.tensors)[::-1]
+        snap.release()
+        back = engine.restore(views)
+        want = _flat(_state(9, wrap=False))[::-1]
+        assert all(torch.equal(plain(a), b) for a, b in zip(back, want))

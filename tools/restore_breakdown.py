@@ -79,7 +79,7 @@ def main():
         out["h2d_pinned_GBps"] = round(8 * (1 << 30) / (time.perf_counter() - t0) / 1e9, 1)
         from nvidia_resiliency_ext.checkpointing.b200.engine import HostBuffer
 
-        hb = HostBuffer.create(4 << 30, name=f"/nvrx_b200_rb_{os.getpid()}", pin=True, device=0, prefault_threads=16)
+        hb = HostBuffer.create(4 << 30, name=f"/nvrx_b200_rbslot_{os.getpid()}", pin=True, device=0, prefault_threads=16)
         fd = os.open(path, os.O_RDONLY)
         for threads in (8, 16, 32, 64):
             t0 = time.perf_counter()
