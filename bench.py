@@ -257,6 +257,12 @@ class EngineArm:
         for snap in list(self.ckpt._pending.values()):
             snap.wait()  # CPU wait on the drain's event: bytes are in pinned host memory
 
+    def trace(self):
+        from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
+
+        tr = SnapshotEngine.get().trace
+        return dict(tr) if tr else None
+
     def finalize(self):
         self.ckpt.finalize_async_save(blocking=True, no_dist=True)
 
@@ -281,6 +287,9 @@ class ReferenceArm:
     def host_safe(self):
         pass  # async_save returned after torch.cuda.synchronize(): the host copies are complete
 
+    def trace(self):
+        return None
+
     def finalize(self):
         self.ckpt.finalize(blocking=True)
 
@@ -288,7 +297,7 @@ class ReferenceArm:
         self.ckpt.finalize(blocking=True)
 
 
-def api_loop(arm, sd, path, steps, warmup, persist_steps):
+def api_loop(arm, sd, path, steps, warmup, persist_steps, trace_rows=None):
     """K checkpoints through ``arm``; per step: stall, time to host-safe, time to persisted (only when the step wrote)."""
     ev = torch.cuda.Event()
     stall, safe, persist = [], [], []
@@ -299,9 +308,16 @@ def api_loop(arm, sd, path, steps, warmup, persist_steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         arm.save(sd, path, write)
+        t_ret = time.perf_counter()
         ev.record()
         ev.synchronize()  # the training stream is free again here
         t1 = time.perf_counter()
+        if it >= warmup and trace_rows is not None:
+            tr = arm.trace()
+            if tr:
+                trace_rows.append({"to_snapshot_ms": (tr["enter"] - t0) * 1e3, "plan_ms": (tr["planned"] - tr["enter"]) * 1e3,
+                                   "enqueue_ms": (tr["launched"] - tr["planned"]) * 1e3, "after_launch_ms": (t_ret - tr["launched"]) * 1e3,
+                                   "gpu_tail_ms": (t1 - t_ret) * 1e3})
         arm.host_safe()
         t2 = time.perf_counter()
         arm.finalize()
@@ -509,7 +525,8 @@ def run_arm(args, rank, world, local):
     arm = (EngineArm if engine_arm else ReferenceArm)(args.narrow)
     out_dir = shm_dir(rank)
     path = out_dir / "ckpt.pt"  # one file per rank, overwritten every step
-    stall, safe, persist = api_loop(arm, sd, path, args.steps, args.warmup, args.persist_steps)
+    trace_rows = [] if os.environ.get("NVRX_B200_TRACE", "0") == "1" else None
+    stall, safe, persist = api_loop(arm, sd, path, args.steps, args.warmup, args.persist_steps, trace_rows)
     clocks.__exit__(None, None, None)
     stall_s = max_over_ranks(mean(stall))  # the K timed steps, mean -> ms_per_step
     safe_s = max_over_ranks(mean(safe))
@@ -591,6 +608,8 @@ def run_arm(args, rank, world, local):
         "verify": check,
         "host_cores_on_box": os.cpu_count(),
     }
+    if trace_rows:
+        line["stall_breakdown_ms"] = {k: round(mean([r[k] for r in trace_rows]), 3) for k in trace_rows[0]}
     if engine_arm:
         peak, peak_src = hbm_peak()
         algo = plan.algorithmic_bytes

@@ -76,6 +76,18 @@ def _passthrough(payload):
     return payload
 
 
+def _use_open_file(writer: FileSystemWriter, open_file: Callable) -> None:
+    """Make ``writer`` open its data files through the user's ``open_file(path, mode)``."""
+    from contextlib import contextmanager
+
+    @contextmanager
+    def create_stream(path, mode):
+        with open_file(os.fspath(path), mode) as stream:
+            yield stream
+
+    writer.fs.create_stream = create_stream
+
+
 def _write_separated(writer: FileSystemWriter, plan: SavePlan, planner, hint: str):
     """``FileSystemWriter.write_data`` with the items split by ``hint``: half as many size-balanced buckets as threads, each
     bucket divided into "FQN starts with the hint" and the rest, one file per non-empty part; files of the hinted part carry
@@ -101,6 +113,12 @@ class FileSystemWriterAsync(FileSystemWriter):
     Flow: ``prepare_write_data`` (trainer: resolve + snapshot) -> ``get_save_function_and_args`` -> the returned function
     runs in a writer process -> ``retrieve_write_results`` -> ``finish`` (coordinator writes ``.metadata``)."""
 
+    # Kept for API compatibility (reference ``filesystem_async.py:161,167``; its tests clear them between cases): the reference
+    # caches "which structures the worker already holds" and its shm staging tensors per writer class; here staging belongs to
+    # the snapshot engine (plans per structure, pooled slots), so both stay empty.
+    _cached_identifiers: set = set()
+    _shm_tensor_cache: Dict = {}
+
     def __init__(
         self,
         path: Union[str, os.PathLike],
@@ -116,7 +134,11 @@ class FileSystemWriterAsync(FileSystemWriter):
             raise NotImplementedError("use_msc (multistorageclient) is not supported by the B200 writer")
         self.checkpoint_dir = path
         self.use_msc = use_msc
-        kwargs.pop("open_file", None)
+        # ``open_file(path, mode)`` (reference ``:214``; its tests inject a failing one to see errors reported): used by the
+        # writer process for this rank's data files instead of PyTorch's own open
+        self.open_file = kwargs.pop("open_file", None)
+        if self.open_file is open:
+            self.open_file = None
         super().__init__(path, *args, **kwargs)
         if not self.single_file_per_rank:
             raise NotImplementedError("single_file_per_rank flag not supported for FileSystemWriterAsync")
@@ -186,8 +208,9 @@ class FileSystemWriterAsync(FileSystemWriter):
 
         self._save_id = uuid.uuid4().hex
         _live_saves.add(self._save_id)
+        options = {"open_file": self.open_file, "multiproc": bool(self.is_multi_proc_io)}
         save_fn = drain_aware(
-            partial(self.write_preloaded_data, self._ctor, int(self.thread_count), self.separation_hint, self._save_id)
+            partial(self.write_preloaded_data, self._ctor, int(self.thread_count), self.separation_hint, (self._save_id, options))
         )
         return save_fn, partial(_passthrough, self._payload), [rank, None, self.results_queue]
 
@@ -199,7 +222,18 @@ class FileSystemWriterAsync(FileSystemWriter):
         ``SystemExit`` / ``KeyboardInterrupt`` (the worker is being aborted) passes through, without a report."""
         outcome = None
         held = []
+        options = {}
+        if isinstance(save_id, tuple):
+            save_id, options = save_id
         try:
+            if options.get("multiproc"):
+                import multiprocessing
+
+                if multiprocessing.current_process().daemon:
+                    # the reference forks one process per file bucket in this mode (``:805-815``), which a daemonic worker
+                    # may not do; the wording is the reference's.  (Here the files are written by threads of PyTorch's
+                    # FileSystemWriter and, for snapshot payloads, by the slot's writer pool -- no extra processes.)
+                    raise RuntimeError("Invalid Setup! User cannot establish a daemon Async worker and then use Multi-Proc File IO.")
             staged = dict(payload["host"])
             for key, blob in list(staged.items()):
                 if isinstance(blob, (bytes, bytearray)):
@@ -221,6 +255,8 @@ class FileSystemWriterAsync(FileSystemWriter):
             # everything is on the host already: keep PyTorch off its CUDA copy-ahead loader (it would create a CUDA
             # context in the writer process, or fail in a forked one)
             writer.per_thread_copy_ahead = 0
+            if options.get("open_file") is not None:
+                _use_open_file(writer, options["open_file"])
             if separation_hint:
                 outcome = _write_separated(writer, payload["plan"], _HostPlanner(staged), separation_hint).wait()
             else:

@@ -661,6 +661,8 @@ class SnapshotEngine:
         self.file_restores = 0  # restores fed straight from the checkpoint file through the pinned ring
         self._aux: Optional[Stream] = None  # checksum kernels (created on first use)
         self._pid = os.getpid()  # forked writers inherit this object; only the creator may tear it down
+        # NVRX_B200_TRACE=1: host-side time stamps of the last snapshot() (enter / planned / launched), for the stall breakdown
+        self.trace: Optional[dict] = {} if os.environ.get("NVRX_B200_TRACE", "0") == "1" else None
 
     # ---- singletons per device ------------------------------------------------------------------
     @classmethod
@@ -792,6 +794,12 @@ class SnapshotEngine:
 
         Returns as soon as the pack kernel and the side-stream copy are *enqueued*.  ``container`` (default: the
         ``NVRX_B200_ZERO_COPY`` switch) packs in checkpoint-container geometry, see :meth:`_plan_for`."""
+        trace = self.trace
+        if trace is not None:
+            import time as _time
+
+            trace.clear()
+            trace["enter"] = _time.perf_counter()
         all_tensors = tensors if isinstance(tensors, list) else list(tensors)
         dev = self.device
         # everything up to the launch is on the training stream's critical path (the stall): one cheap test for the common
@@ -816,6 +824,8 @@ class SnapshotEngine:
             container = False
         plan = self._plan_for(cuda_tensors, mask, container)
 
+        if trace is not None:
+            trace["planned"] = _time.perf_counter()
         stream = self._current_stream()
         staging = self._ensure_staging(plan.staging_bytes)
         tail_room = 0
@@ -866,6 +876,8 @@ class SnapshotEngine:
                 ),
                 "nvrx_snapshot",
             )
+        if trace is not None:
+            trace["launched"] = _time.perf_counter()
         self.launches += (plan.last_launches() if not self.timing else 1) if plan.n_tiles else 0
         slot.drained_total = base + plan.staging_bytes
         self._staging_free = slot.done_event

@@ -459,3 +459,46 @@ def test_result_of_an_abandoned_save_is_not_taken_for_the_next_one(tmp_path, dis
         _loaded_equals(tmp_path / "next", _state())
     finally:
         q.close()
+
+
+def _failing_open(path, mode="rb"):
+    raise OSError("worker critical failure during open()")
+
+
+def _counting_open(path, mode="rb"):
+    with open(os.path.join(os.path.dirname(path), "opened.log"), "a") as log:
+        log.write(os.path.basename(path) + "\n")
+    return open(path, mode)
+
+
+def test_open_file_hook_and_daemon_multiproc_setup(tmp_path, dist_1rank):
+    """Reference tests/checkpointing/unit/test_async_writer.py:180-231: a user ``open_file`` is what the writer process opens this
+    rank's files with (a failing one surfaces as "Worker failure" at finalize); multi-process file IO from a daemonic worker is
+    reported as "Invalid Setup!"."""
+    from torch.distributed.checkpoint import CheckpointException
+
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.filesystem_async import FileSystemWriterAsync
+
+    FileSystemWriterAsync._cached_identifiers.clear()
+    FileSystemWriterAsync._shm_tensor_cache.clear()
+    q = AsyncCallsQueue(persistent=False)
+    try:
+        _async_save(_state(), tmp_path / "counted", q, writer_kw={"open_file": _counting_open})
+        q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+        assert any(n.endswith(".distcp") for n in (tmp_path / "counted" / "opened.log").read_text().split())
+        _loaded_equals(tmp_path / "counted", _state())
+        _async_save(_state(), tmp_path / "broken", q, writer_kw={"open_file": _failing_open})
+        with pytest.raises(CheckpointException) as err:
+            q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+        assert "Worker failure" in str(err.value)
+    finally:
+        q.close()
+    q = AsyncCallsQueue(persistent=True, is_daemon=True)
+    try:
+        _async_save(_state(), tmp_path / "daemon", q, writer_kw={"is_multiproc_io": True})
+        with pytest.raises(CheckpointException) as err:
+            q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+        assert "Invalid Setup!" in str(err.value)
+    finally:
+        q.close()
