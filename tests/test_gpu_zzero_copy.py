@@ -103,7 +103,18 @@ def test_restore_through_pread(tmp_path, shm_dir, dist_1rank, built_library, mon
         assert mgr.find_latest() == 4
         from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
 
-        before = SnapshotEngine.get().file_restores
+        eng = SnapshotEngine.get()
+        before = eng.file_restores + eng.resident_restores
         loaded, _ = mgr.load()
         assert _equal(loaded.state_dict, _state(55)) and all(t.is_cuda for t in loaded.tensors)
-        assert SnapshotEngine.get().file_restores == before + 1
+        # from the file through the ring, or -- on /dev/shm, where the file IS a still-pinned slot of this process -- in place
+        assert eng.file_restores + eng.resident_restores == before + 1
+        mgr_fresh = LocalCheckpointManager(root)
+        os.environ["NVRX_B200_ZERO_COPY"] = "0"  # what a freshly started process sees: no resident slot, the file path
+        try:
+            assert mgr_fresh.find_latest() == 4
+            files = eng.file_restores
+            loaded, _ = mgr_fresh.load()
+            assert _equal(loaded.state_dict, _state(55)) and eng.file_restores == files + 1
+        finally:
+            os.environ["NVRX_B200_ZERO_COPY"] = "1"
