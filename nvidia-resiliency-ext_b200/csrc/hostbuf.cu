@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "nvrx_snap.h"
+#include "host_numa.h"
 
 extern "C" size_t nvrx_crc32_fold(uint32_t* crc, const uint8_t* p, size_t n);  // crc32_fold.cpp (not part of the ABI)
 
@@ -78,42 +79,6 @@ void write_slot_prefix(uint8_t* page) {
     put16(page + 30 + name_len, 0x4246);  // "FB": the extra-field id PyTorch uses for alignment padding
     put16(page + 32 + name_len, static_cast<uint16_t>(extra_len - 4));
     static_assert(30 + sizeof(name) - 1 + 4 <= kHeaderOff, "zip prefix must end before the Header struct");
-}
-
-// CPUs of the NUMA node the GPU hangs off (empty set if sysfs does not say): the slot is first-touched from
-// those CPUs so its pages land in the DRAM next to the GPU's PCIe root port and the drain does not cross sockets.
-bool numa_cpus_of_device(int device, cpu_set_t* set) {
-    char bdf[32] = {0};
-    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) return false;
-    for (char* c = bdf; *c; ++c) *c = static_cast<char>(tolower(*c));
-    char path[128];
-    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
-    FILE* f = fopen(path, "r");
-    if (!f) return false;
-    int node = -1;
-    const int got = fscanf(f, "%d", &node);
-    fclose(f);
-    if (got != 1 || node < 0) return false;
-    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
-    f = fopen(path, "r");
-    if (!f) return false;
-    char list[4096] = {0};
-    const bool ok = fgets(list, sizeof(list), f) != nullptr;
-    fclose(f);
-    if (!ok) return false;
-    CPU_ZERO(set);
-    int count = 0;
-    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
-        int lo = 0, hi = 0;
-        const int n = sscanf(tok, "%d-%d", &lo, &hi);
-        if (n == 1) hi = lo;
-        if (n < 1) continue;
-        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) {
-            CPU_SET(c, set);
-            ++count;
-        }
-    }
-    return count > 0;
 }
 
 void prefault(uint8_t* base, uint64_t bytes, int threads, const cpu_set_t* cpus) {
@@ -265,7 +230,7 @@ int nvrx_hostbuf_create(const char* shm_name, uint64_t bytes, int prefault_threa
     if (shm_name) hb->name = shm_name;
     if (prefault_threads > 0) {
         cpu_set_t cpus;
-        const bool local = pin && !getenv("NVRX_B200_NO_NUMA") && numa_cpus_of_device(device, &cpus);
+        const bool local = pin && !getenv("NVRX_B200_NO_NUMA") && nvrx::numa_cpus_of_device(device, &cpus);
         prefault(hb->map, total, prefault_threads, local ? &cpus : nullptr);
     }
     write_slot_prefix(hb->map);

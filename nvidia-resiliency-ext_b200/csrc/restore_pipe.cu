@@ -22,7 +22,10 @@
 #include <thread>
 #include <vector>
 
+#include <sys/mman.h>
+
 #include "nvrx_snap.h"
+#include "host_numa.h"
 
 #define NVRX_CUDA(expr)                                       \
     do {                                                      \
@@ -34,6 +37,8 @@ namespace {
 
 struct Ring {  // one per device, kept for the life of the process (page-locking is the expensive part)
     uint8_t* base = nullptr;
+    bool have_cpus = false;  // CPUs of the NUMA node the GPU hangs off: readers run there, the ring was first touched there
+    cpu_set_t cpus;
     uint64_t chunk = 0;
     int slots = 0;
     std::vector<cudaEvent_t> sent;  // H2D of the chunk that last used the slot
@@ -47,12 +52,32 @@ int ring_for(int device, uint64_t chunk, int slots, Ring** out) {
     if (r.base && (r.chunk != chunk || r.slots != slots)) {
         for (cudaEvent_t ev : r.sent) cudaEventDestroy(ev);
         r.sent.clear();
-        cudaFreeHost(r.base);
+        cudaHostUnregister(r.base);
+        munmap(r.base, r.chunk * static_cast<uint64_t>(r.slots));
         r.base = nullptr;
     }
     if (!r.base) {
-        void* p = nullptr;
-        NVRX_CUDA(cudaHostAlloc(&p, chunk * static_cast<uint64_t>(slots), cudaHostAllocPortable));
+        // anonymous pages first touched from the CPUs next to the GPU (so the reads land in, and the H2D leaves from, the DRAM
+        // behind the GPU's PCIe root port), then page-locked -- the same placement the snapshot slots get (hostbuf.cu)
+        const uint64_t bytes = chunk * static_cast<uint64_t>(slots);
+        void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p == MAP_FAILED) return NVRX_E_NOMEM;
+        r.have_cpus = !getenv("NVRX_B200_NO_NUMA") && nvrx::numa_cpus_of_device(device, &r.cpus);
+        {
+            uint8_t* b = static_cast<uint8_t*>(p);
+            const bool bind = r.have_cpus;
+            const cpu_set_t cpus = r.cpus;
+            std::thread toucher([=] {
+                if (bind) sched_setaffinity(0, sizeof(cpu_set_t), &cpus);
+                for (uint64_t o = 0; o < bytes; o += 4096) b[o] = 0;
+            });
+            toucher.join();
+        }
+        cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+        if (e != cudaSuccess) {
+            munmap(p, bytes);
+            return static_cast<int>(e);
+        }
         r.base = static_cast<uint8_t*>(p);
         r.chunk = chunk;
         r.slots = slots;
@@ -152,6 +177,7 @@ int nvrx_fill_from_fd(void* staging, uint64_t staging_bytes, int fd, int64_t n, 
     const uint64_t total_pieces = pieces.size();
 
     auto reader = [&] {
+        if (ring->have_cpus) sched_setaffinity(0, sizeof(cpu_set_t), &ring->cpus);  // this thread only; it ends with the call
         while (!err.load(std::memory_order_relaxed)) {
             const uint64_t i = next.fetch_add(1);
             if (i >= total_pieces) break;

@@ -1067,9 +1067,14 @@ class SnapshotEngine:
         """File -> GPU tensors without a snapshot-sized host buffer (``nvrx_fill_from_fd``): a pool of readers fills a small
         ring of pinned chunks from the checkpoint file while the chunks already read travel to the device; one scatter
         kernel at the end.  A freshly restarted process does not have to create and page-lock a 16 GB slot first (~2 s)."""
+        import time as _time
+
         path, file_offs = file_source
+        t0 = _time.perf_counter()
         plan = self._plan_for(out, mask)
+        t1 = _time.perf_counter()
         staging = self._ensure_staging(plan.staging_bytes)
+        t2 = _time.perf_counter()
         live = [(off, nb, fo) for off, nb, fo in zip(plan.offsets, plan.packed_nbytes, file_offs) if nb]
         stream = self._current_stream()
         if self._staging_free is not None:
@@ -1086,6 +1091,7 @@ class SnapshotEngine:
             )
         finally:
             os.close(fd)
+        t3 = _time.perf_counter()
         plan.scatter(staging.ptr, stream)
         self.launches += 1 if plan.n_tiles else 0
         self.file_restores += 1
@@ -1093,6 +1099,8 @@ class SnapshotEngine:
         done.record(stream)
         self._staging_free = done
         done.synchronize()  # restore is a blocking call like the reference's
+        if self.trace is not None:
+            self.trace["restore"] = {"plan_s": t1 - t0, "staging_s": t2 - t1, "file_to_device_s": t3 - t2, "scatter_s": _time.perf_counter() - t3}
         return out
 
     def resident_source(self, path, host_tensors: Sequence[torch.Tensor]) -> Optional[Tuple[_Slot, List[int]]]:

@@ -89,13 +89,21 @@ def main():
         hb.close()
         # the whole public call
         del loaded, host
-        mgr2 = LocalCheckpointManager(root)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        mgr2.find_latest()
-        back, _ = mgr2.load()
-        torch.cuda.synchronize()
-        out["find_latest_plus_load_s"] = round(time.perf_counter() - t0, 3)
+        del dev
+        torch.cuda.empty_cache()
+        for label in ("first", "second"):
+            mgr2 = LocalCheckpointManager(root)
+            engine.trace = {}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mgr2.find_latest()
+            t1 = time.perf_counter()
+            back, _ = mgr2.load()
+            torch.cuda.synchronize()
+            out[f"find_latest_plus_load_s_{label}"] = round(time.perf_counter() - t0, 3)
+            out[f"find_latest_s_{label}"] = round(t1 - t0, 3)
+            out[f"load_stages_{label}"] = {k: round(v, 3) for k, v in engine.trace.get("restore", {}).items()}
+            del back
     finally:
         shutil.rmtree(root, ignore_errors=True)
     print(json.dumps(out), flush=True)
