@@ -54,9 +54,20 @@ def test_reference_local_checkpoint_tests(world):
     assert " passed" in out and "failed" not in out
 
 
+DCP_GROUPS = ["test_async_is_equivalent_to_sync", "test_invalid_async_setup", "test_errors_are_reported", "test_cached_metadata",
+              "test_cached_data_structure", "test_cpu_shm_for_gpu_tensors", "test_async_cp_with_multiple_queue_and_abort"]
+
+
 @pytest.mark.parametrize("world", [1, 2])
 def test_reference_dcp_async_writer_tests(world):
+    """All 13 cases of the reference's test_async_writer.py (the last -k pattern also selects ..._followed_by_delete).  Each
+    group runs in a process of its own with its own time limit: in one process the file did not finish within 900 s on the
+    B200 box in round 2 (cause not found yet; every group passes on its own, profiles/r02_reference_dcp_tests.log)."""
     if world not in worlds():
         pytest.skip(f"needs >= {world} CUDA devices")
-    out = run_reference_tests(["test_async_writer.py"], world, timeout=1500)
-    assert " passed" in out and "failed" not in out
+    passed = 0
+    for group in DCP_GROUPS:
+        out = run_reference_tests(["test_async_writer.py"], world, ["-k", group], timeout=300)
+        assert " passed" in out and "failed" not in out, group
+        passed += int(out.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
+    assert passed == 13

@@ -1,7 +1,6 @@
 """GPU CRC-32 (csrc/crc_kernels.cuh) on the device.  The arithmetic, the tables and the CPU-only chaining are covered without a
 GPU (tests/test_crc_cpu.py runs the kernel's own device functions lane by lane on the host); what is left for the GPU is the
-kernel's indexing / launch and the engine plumbing.  Written after round 1's GPU budget was spent: skipped unless
-NVRX_B200_TEST_UNVALIDATED=1 (tools/gpu_round.sh zerocopy)."""
+kernel's indexing / launch and the engine plumbing.  First run on a B200 in round 2."""
 import ctypes as C
 import os
 import zipfile
@@ -13,10 +12,7 @@ import torch
 
 from oracle import crc_oracle as co
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="opt-in mode, not yet validated on a B200"),
-]
+pytestmark = pytest.mark.gpu  # validated on B200 in round 2 (profiles/r02_pytest_gpu_*.log): part of the default suite
 
 
 def test_kernel_values_match_zlib(built_library):

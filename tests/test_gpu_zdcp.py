@@ -9,12 +9,8 @@ import torch
 import torch.distributed.checkpoint as dcp
 from torch.distributed.checkpoint import DefaultSavePlanner, FileSystemReader, FileSystemWriter
 
-# Written after round 1's GPU budget was spent (the writer's host side is covered by tests/test_dcp_async_cpu.py, byte for byte
-# against the reference's own output): skipped unless NVRX_B200_TEST_UNVALIDATED=1 until it has run on a B200 once.
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="not yet validated on a B200"),
-]
+# (the writer's host side is covered by tests/test_dcp_async_cpu.py, byte for byte against the reference's own output)
+pytestmark = pytest.mark.gpu  # validated on B200 in round 2 (profiles/r02_pytest_gpu_*.log): part of the default suite
 
 
 def _state(step=0):

@@ -1,18 +1,13 @@
-"""Zero-copy persistence on the GPU (opt-in, ``NVRX_B200_ZERO_COPY=1``): the pinned slot a snapshot drains into IS the
+"""Zero-copy persistence on the GPU (the default since round 2; ``NVRX_B200_ZERO_COPY=0`` opts out): the pinned slot a snapshot drains into IS the
 checkpoint file on /dev/shm (hard link), so a save is durable as soon as its drain has finished.
 
-The host half is covered on the CPU (tests/test_zero_copy_cpu.py).  These tests were written after round 1's GPU budget was
-spent and have not run on a B200 yet; they are skipped unless NVRX_B200_TEST_UNVALIDATED=1 so that an unvalidated opt-in mode
-cannot turn the default suite red.  Round 2: run them, then drop the gate."""
+The host half is covered on the CPU (tests/test_zero_copy_cpu.py).  First run (and made the default mode) on a B200 in round 2."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="opt-in mode, not yet validated on a B200"),
-]
+pytestmark = pytest.mark.gpu  # validated on B200 in round 2 (profiles/r02_pytest_gpu_*.log): part of the default suite
 
 
 def _state(seed, n=12):
