@@ -42,15 +42,13 @@ class TorchAsyncCheckpoint(object):
             request = AsyncRequest(TorchAsyncCheckpoint.async_fn, (preload_tensors(state_dict), *args), [], kwargs or {})
             self._async_calls_queue.schedule_async_request(request)
             return
-        devices = {t.get_device() for t in cuda}
-        if len(devices) != 1:
-            raise ValueError("async_save: the CUDA tensors of the state dict must live on one device")
         from ..b200.engine import SnapshotEngine
 
         # GPU work first (pack sub-launches + drain are enqueued here), Python bookkeeping while it runs.  Host tensors in the
         # same dict (e.g. ``torch.get_rng_state()``) travel to the writer as they are, like in the reference, whose
         # ``preload_tensors`` maps them through ``.to("cpu")`` = identity (``utils.py:93-94``).
-        snap = SnapshotEngine.get(devices.pop()).snapshot(cuda, narrow=self._narrow)
+        # (the engine checks that all of them live on ONE device and raises ValueError otherwise)
+        snap = SnapshotEngine.get(cuda[0].get_device()).snapshot(cuda, narrow=self._narrow)
         counter = iter(range(len(cuda)))
 
         def leaf(v):

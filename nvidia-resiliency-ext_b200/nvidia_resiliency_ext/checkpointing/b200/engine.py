@@ -757,10 +757,10 @@ class SnapshotEngine:
         default, so that the drained slot can be published as a file without a copy.  ``offsets``: explicit staging
         offsets (restore straight from a published slot)."""
         nbytes = [t.nbytes for t in tensors]
-        dtypes = [t.dtype for t in tensors]
         if narrow is not None and not any(narrow):
             narrow = None
-        key = (tuple(nbytes), tuple(dtypes), tuple(narrow) if narrow is not None else None)
+        # a bit copy does not care about dtypes (the layout handed to readers does: it is validated where it is cached)
+        key = (tuple(nbytes), tuple(narrow) if narrow is not None else None)
         if offsets is not None:
             key = ("at", tuple(offsets)) + key
         elif container:
@@ -808,6 +808,8 @@ class SnapshotEngine:
         cuda_tensors = all_tensors
         if not all([t.get_device() == dev for t in all_tensors]):
             passthrough = {i: t for i, t in enumerate(all_tensors) if t.get_device() != dev}
+            if any(t.is_cuda for t in passthrough.values()):
+                raise ValueError("snapshot: the CUDA tensors must live on one device (the engine's)")
             cuda_tensors = [t for i, t in enumerate(all_tensors) if i not in passthrough]
         # the kernel walks contiguous byte ranges; strided tensors are compacted first (rare)
         if not all([t.is_contiguous() for t in cuda_tensors]):
@@ -901,8 +903,9 @@ class SnapshotEngine:
 
         # the layout only depends on the plan and the shapes: built once per (plan, shapes), not per snapshot
         shapes = [t.shape for t in cuda_tensors]
+        dtypes = [t.dtype for t in cuda_tensors]
         cached = plan.__dict__.get("_layout")
-        if cached is not None and cached[0] == shapes:
+        if cached is not None and cached[0] == shapes and cached[2] == dtypes:
             layout = cached[1]
         else:
             layout = PackedLayout(
@@ -915,7 +918,7 @@ class SnapshotEngine:
                 total_bytes=plan.staging_bytes,
                 align=self.align,
             )
-            plan.__dict__["_layout"] = (shapes, layout)
+            plan.__dict__["_layout"] = (shapes, layout, dtypes)
         return Snapshot(
             engine=self, slot=slot, layout=layout, progress_target=slot.drained_total, passthrough=passthrough,
             n_total=len(all_tensors), pack_start=start, pack_stop=stop, crc_info=crc_info,
