@@ -422,7 +422,7 @@ def local_manager_leg(arm_name, sd, tensors, total, rank, narrow):
 
             from nvidia_resiliency_ext.checkpointing.b200.engine import SnapshotEngine
 
-            mgr = LocalCheckpointManager(root, session_id=f"r{rank}")
+            mgr = LocalCheckpointManager(root, session_id="bench")
             q = AsyncCallsQueue(persistent=False)
             # like TorchAsyncCheckpoint.warmup(): staging and host slot for THIS state exist before the timed save (the async
             # loop above may have run on narrowed, i.e. smaller, snapshots; the reference arm's pinned cache is warm from its loop)
@@ -440,7 +440,7 @@ def local_manager_leg(arm_name, sd, tensors, total, rank, narrow):
             t2 = time.perf_counter()
             q.close()
             del tasd, req
-            mgr2 = LocalCheckpointManager(root, session_id=f"r{rank}")
+            mgr2 = LocalCheckpointManager(root, session_id="bench")
             torch.cuda.synchronize()
             dist.barrier()
             t3 = time.perf_counter()

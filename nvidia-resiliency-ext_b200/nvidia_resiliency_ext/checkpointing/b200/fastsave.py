@@ -190,12 +190,30 @@ def save(obj, f, *args, **kwargs) -> str:
         # in by offset -- the stock writer handles those (checked BEFORE anything is emitted into f)
         torch.save(obj, f, **kwargs)
         return "torch"
-    with torch.serialization.skip_data():
-        torch.save(obj, f, **kwargs)
+    # A path is filled under a private name and renamed into place when complete: several ranks saving to ONE path (the
+    # reference's own test does, tests/checkpointing/unit/test_async_save.py:38) must not truncate the file another writer
+    # has mapped (SIGBUS in that writer), and readers never see a half-written checkpoint.
+    final = scratch = None
+    if is_path:
+        # (same base name inside a scratch directory: PyTorch names the archive inside the zip after the file)
+        scratch = os.path.join(os.path.dirname(os.path.abspath(name)), f".nvrx_tmp_{os.getpid()}_{os.urandom(4).hex()}")
+        os.mkdir(scratch)
+        final, name = name, os.path.join(scratch, os.path.basename(name))
+        f = name
+    try:
+        with torch.serialization.skip_data():
+            torch.save(obj, f, **kwargs)
+    except BaseException:
+        if scratch is not None:
+            import shutil
+
+            shutil.rmtree(scratch, ignore_errors=True)
+        raise
     if not is_path:
         f.flush()
     reader = torch._C.PyTorchFileReader(os.fspath(name))
     fd = os.open(name, os.O_RDWR)  # a descriptor of our own, read+write: the writer maps the range, the checksum patch reads
+    ok = False
     try:
         by_slot = {}
         patch, patch_crcs = [], []  # records whose checksum is known here: (name, data offset, size)
@@ -229,7 +247,19 @@ def save(obj, f, *args, **kwargs) -> str:
             from . import ptzip
 
             ptzip.patch_record_crcs(fd, patch, patch_crcs)
+        ok = True
     finally:
         del reader
         os.close(fd)
+        if final is not None:
+            try:
+                if ok:
+                    os.replace(name, final)
+                else:
+                    os.unlink(name)
+            finally:
+                try:
+                    os.rmdir(scratch)
+                except OSError:
+                    pass
     return "parallel"

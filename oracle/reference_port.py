@@ -126,11 +126,15 @@ def reference_local_load(path):
 
 # ---- replication ---------------------------------------------------------------------------------------------------
 class _Placeholder:
+    """``TensorPlaceholder`` (local/replication/torch_device_utils.py:43-99): shape / dtype travel, of the device only its TYPE --
+    the receiver allocates on ITS default device of that type."""
+
     def __init__(self, t: torch.Tensor):
-        self.shape, self.dtype, self.device = t.shape, t.dtype, t.device
+        self.shape, self.dtype, self.device_type = t.shape, t.dtype, t.device.type
 
     def empty_like(self):
-        return torch.empty(self.shape, dtype=self.dtype, device=self.device)
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device_type == "cuda" else torch.device(self.device_type)
+        return torch.empty(self.shape, dtype=self.dtype, device=dev)
 
 
 def reference_all_gather_batch(my_tensors: Sequence[torch.Tensor], group=None, target_device: Optional[str] = "cpu") -> List[List[torch.Tensor]]:

@@ -342,3 +342,38 @@ def test_writer_reports_a_full_file_system_as_an_error(built_library, tmp_path):
         signal.signal(signal.SIGXFSZ, old_handler)
         os.close(fd)
         hb.close()
+
+
+def _save_repeatedly(path, seed, rounds):
+    from nvidia_resiliency_ext.checkpointing.b200 import fastsave
+    from nvidia_resiliency_ext.checkpointing.b200.engine import HostBuffer
+
+    hb = HostBuffer.create(8 << 20, name=f"/nvrx_race_{os.getpid()}", pin=False, prefault_threads=1)
+    try:
+        v = hb.segment(0, 4 << 20, torch.float32, (1 << 20,))
+        v.fill_(float(seed))
+        with fastsave.slot_ranges([(hb.data_ptr, hb.capacity, hb)]):
+            for _ in range(rounds):
+                assert fastsave.save({"v": v, "who": seed}, path) == "parallel"
+        del v
+    finally:
+        hb.close()
+
+
+def test_several_writers_on_one_path_do_not_hurt_each_other(built_library, tmp_path):
+    """The reference's own test saves the same path from every rank (tests/checkpointing/unit/test_async_save.py:38).  A writer
+    that truncates the file another one has mapped kills that one with SIGBUS (seen at world size 2 on the B200 box): every
+    writer fills a private file and renames it into place."""
+    import multiprocessing as mp
+
+    path = tmp_path / "shared.pt"
+    ctx = mp.get_context("fork")
+    procs = [ctx.Process(target=_save_repeatedly, args=(path, seed, 6)) for seed in (1, 2, 3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert [p.exitcode for p in procs] == [0, 0, 0]
+    got = torch.load(path)
+    assert got["who"] in (1, 2, 3) and torch.all(got["v"] == float(got["who"]))  # one writer's complete file, not a mix
+    assert sorted(x.name for x in tmp_path.iterdir()) == ["shared.pt"]  # no scratch directories left behind
