@@ -321,12 +321,11 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
         for m, meta in zip(self._members, metas):
             lo, hi = (0, 0) if m == me else fragment_range(meta["total"], meta["shard_bytes"], self._others(m).index(me))
             recv_sizes.append(hi - lo)
-        # Measured (profiles/r01_c4_kernel_only_*gpu.json, 16 GB/rank): with 2 members the fused kernel beats pack + NCCL
-        # (23.3 vs 34.0 ms); with 8 members every rank walks its fragments in the same order, so all senders hit the same
-        # destination at the same time (incast) and it loses (70.4 vs 29.9 ms).  Until the walk is rotated per rank the
-        # fused path is the default only for pairs; NVRX_B200_EXCHANGE=p2p forces it.
-        if bases is not None and not (n == 1 or xch._exchange_mode() == "p2p"):
-            bases = None
+        # Round 1 (profiles/r01_c4_kernel_only_*gpu.json, 16 GB/rank): with 2 members the fused kernel beat pack + NCCL (23.3 vs
+        # 34.0 ms); with 8 members every rank walked its fragments in the same order, all senders hit the same destination at
+        # the same time (incast) and it lost (70.4 vs 29.9 ms).  Since round 2 the tile list of a sharded plan interleaves the
+        # fragments (destination-major order, csrc/snap_api.cu build_tiles), every GPU stores to all peers at once, and the
+        # fused kernel is the default whenever the clique is NVLink-peer reachable; NVRX_B200_EXCHANGE=nccl keeps pack + NCCL.
         if bases is not None:
             # fused: own copy -> staging, fragment k -> member k's exchange buffer (slot = my index among its senders)
             dest = []

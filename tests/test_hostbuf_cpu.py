@@ -367,7 +367,7 @@ def test_several_writers_on_one_path_do_not_hurt_each_other(built_library, tmp_p
     import multiprocessing as mp
 
     path = tmp_path / "shared.pt"
-    ctx = mp.get_context("fork")
+    ctx = mp.get_context("spawn")  # (fork of this multi-threaded test process + OpenMP in the child does not end well)
     procs = [ctx.Process(target=_save_repeatedly, args=(path, seed, 6)) for seed in (1, 2, 3)]
     for p in procs:
         p.start()
