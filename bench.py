@@ -426,7 +426,10 @@ def local_manager_leg(arm_name, sd, tensors, total, rank, narrow):
             q = AsyncCallsQueue(persistent=False)
             # like TorchAsyncCheckpoint.warmup(): staging and host slot for THIS state exist before the timed save (the async
             # loop above may have run on narrowed, i.e. smaller, snapshots; the reference arm's pinned cache is warm from its loop)
-            SnapshotEngine.get().reserve(sum(t.numel() * t.element_size() for t in tensors) + (len(tensors) + 8) * 1024)
+            eng = SnapshotEngine.get()
+            need = sum(t.numel() * t.element_size() for t in tensors) + (len(tensors) + 8) * 4096
+            eng._ensure_staging(need)
+            eng._release(eng._acquire_slot(need))  # one free slot that is large enough (a no-op when the async loop left one)
             tasd = BasicTensorAwareStateDict(fresh_containers(sd))
             torch.cuda.synchronize()
             dist.barrier()
