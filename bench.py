@@ -385,27 +385,63 @@ def stall_beside_training(arm, sd, path, loop, reps, before=10, after=30):
     return (median(with_ckpt) - median(base)) * 1e3, median(base) * 1e3
 
 
-def d2h_ceiling(dev, world, gb=16.0):
-    """What the box gives N concurrent plain device->pinned-host copies (cudaMemcpyAsync into cudaHostAlloc memory, all
-    ranks at once): the PCIe / host-memory ceiling the e2e number can be judged against."""
-    n = 1 << 30
-    src = torch.empty(n, dtype=torch.uint8, device=dev)
-    dst = torch.empty(n, dtype=torch.uint8).pin_memory()
-    reps = max(1, int(gb))
-    for _ in range(2):
+def _numa_cpus_of_gpu(index):
+    """CPUs of the NUMA node GPU ``index`` hangs off (sysfs), or None."""
+    try:
+        props = torch.cuda.get_device_properties(index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        return cpus or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def d2h_ceiling(dev, world, gib=4, reps=4):
+    """What the box gives N concurrent plain device->pinned-host copies (cudaMemcpyAsync into a cudaHostAlloc buffer, all
+    ranks at once): the PCIe / host-memory ceiling the e2e number can be judged against.  The buffer is allocated while the
+    thread is bound to the CPUs next to the GPU: where a pinned buffer lands is otherwise a lottery, and a buffer on the other
+    socket halves the rate when all 8 GPUs copy (16-21 instead of 39 GB/s per GPU on this pool's 8-GPU box,
+    profiles/r02_d2h_ceiling_8gpu.jsonl)."""
+    n, rate, err, cpus, src, dst = gib << 30, None, None, None, None, None
+    try:
+        src = torch.empty(n, dtype=torch.uint8, device=dev)
+        cpus, before = _numa_cpus_of_gpu(dev.index), None
+        try:
+            if cpus:
+                before = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, cpus)
+            dst = torch.empty(n, dtype=torch.uint8).pin_memory()
+            dst.fill_(0)
+        finally:
+            if before is not None:
+                os.sched_setaffinity(0, before)
         dst.copy_(src, non_blocking=True)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    except Exception as exc:  # noqa: BLE001 - a ceiling that cannot be measured must not take the bench line with it
+        err = exc
+    dist.barrier()  # (every rank reaches the collectives whatever happened to its own measurement)
+    if err is None:
+        try:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            rate = reps * n / (time.perf_counter() - t0) / 1e9
+        except Exception as exc:  # noqa: BLE001
+            err = exc
     dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        dst.copy_(src, non_blocking=True)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    dist.barrier()
-    rate = reps * n / dt / 1e9
+    if min_over_ranks(0.0 if rate is None else 1.0) < 0.5:
+        return {"per_gpu_min_GBps": None, "per_gpu_max_GBps": None, "what": f"not measured on every rank ({err!r})"}
     return {"per_gpu_min_GBps": round(min_over_ranks(rate), 2), "per_gpu_max_GBps": round(max_over_ranks(rate), 2),
-            "what": f"{world} concurrent torch pinned-memory D2H copies, {reps} x 1 GiB each (cudaHostAlloc buffer, plain cudaMemcpyAsync)"}
+            "what": f"{world} concurrent plain pinned-memory D2H copies, {reps} x {gib} GiB each (cudaHostAlloc buffer on the GPU's NUMA "
+                    f"node{'' if cpus else ' -- node unknown, unbound'}, cudaMemcpyAsync)"}
 
 
 def local_manager_leg(arm_name, sd, tensors, total, rank, narrow):

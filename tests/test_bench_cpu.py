@@ -1,0 +1,90 @@
+"""bench.py's measurement loops executed on the CPU (stand-in device at the C-ABI boundary, gloo, small state): the driver runs
+bench.py on boxes this container cannot reach, so every leg both arms share -- api_loop, the local-manager leg, the JSON
+assembly helpers -- is at least executed here.  Numbers are meaningless; only "it runs and verifies" is checked."""
+import sys
+import types
+from pathlib import Path
+
+import pytest
+import torch
+
+from _fake_device import FakeCudaTensor, fake_device
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+class _Event:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+@pytest.fixture
+def bench(monkeypatch):
+    sys.path.insert(0, str(ROOT))
+    import bench as B
+
+    monkeypatch.setattr(B, "max_over_ranks", lambda x: float(x))
+    monkeypatch.setattr(B, "min_over_ranks", lambda x: float(x))
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    return B
+
+
+def _small_state(fake=True):
+    g = torch.Generator().manual_seed(3)
+    wrap = FakeCudaTensor.wrap if fake else (lambda t: t)
+    model = {f"l{i}": wrap(torch.randn(65 + i, 33, generator=g)) for i in range(4)}
+    opt = {i: {"exp_avg": wrap(torch.randn(65 + i, 33, generator=g)), "step": wrap(torch.tensor(float(i)))} for i in range(4)}
+    return {"model": model, "optimizer": {"state": opt}}
+
+
+def test_engine_arm_loops(bench, monkeypatch, built_library, shm_dir, dist_1rank):
+    B = bench
+    with fake_device(monkeypatch) as (engine, lib):
+        sd = _small_state()
+        tensors = B.flatten(sd)
+        total = sum(t.numel() * t.element_size() for t in tensors)
+        arm = B.EngineArm(False)
+        try:
+            rows = []
+            stall, safe, persist = B.api_loop(arm, sd, shm_dir / "ckpt.pt", steps=3, warmup=1, persist_steps=1, trace_rows=rows)
+            assert len(stall) == len(safe) == len(persist) == 3 and all(0 < a <= b <= c for a, b, c in zip(stall, safe, persist))
+            loaded = B.flatten(torch.load(shm_dir / "ckpt.pt", weights_only=False))
+            assert len(loaded) == len(tensors) and all(B.bits_equal(a, b.as_subclass(torch.Tensor)) for a, b in zip(loaded, tensors))
+        finally:
+            arm.close()
+        leg = B.local_manager_leg("engine", sd, tensors, total, 0, False)
+        assert leg["restore_verify"] == "bit-exact" and leg["restore_s"] > 0 and leg["local_save_persist_s"] >= leg["local_save_stall_ms"] / 1e3
+        assert not any(s.busy for s in engine._slots)
+
+
+def test_reference_arm_loops(bench, tmp_path, dist_1rank, monkeypatch):
+    B = bench
+    sd = _small_state(fake=False)
+    arm = B.ReferenceArm(False)
+    stall, safe, persist = B.api_loop(arm, sd, tmp_path / "ref.pt", steps=3, warmup=1, persist_steps=2)
+    arm.close()
+    assert len(stall) == 3 and len(persist) == 2 and arm.trace() is None
+    got = B.flatten(torch.load(tmp_path / "ref.pt", weights_only=False))
+    assert all(B.bits_equal(a, b) for a, b in zip(got, B.flatten(sd)))
+    # the local leg of the reference arm restores with tensor.to("cuda"): only its save half runs without a GPU
+    from oracle import reference_port as rp
+
+    res = rp.reference_local_save(B.fresh_containers(sd), tmp_path / "iter_0000001_0_local.pt")
+    assert res["total"] >= res["stall"] > 0
+
+
+def test_workload_matches_the_survey():
+    sys.path.insert(0, str(ROOT))
+    import bench as B
+
+    shapes = B.llama3_8b_shard_shapes()
+    params = sum(int(torch.tensor(s).prod()) for _, s in shapes)
+    assert len(shapes) == 291 and params == 1_003_782_656  # 1/8 row shard of Llama-3-8B
+    assert set(B.WORKLOADS) == {"c2", "c3"} and "16.06 GB" in B.WORKLOADS["c2"]

@@ -531,3 +531,54 @@ def test_restoring_the_state_dict_that_was_just_saved(monkeypatch, built_library
         back = engine.restore(views)
         want = _flat(_state(9, wrap=False))[::-1]
         assert all(torch.equal(plain(a), b) for a, b in zip(back, want))
+
+
+from test_ptl_glue_cpu import glue  # noqa: E402,F401  (fixture: stub of the three lightning symbols the glue imports)
+
+
+def test_ptl_glue_drives_the_local_manager(glue, monkeypatch, built_library, shm_dir, dist_1rank):  # noqa: F811
+    """CPU twin of tests/test_gpu_api.py::test_ptl_glue_drives_the_local_manager_on_gpu (same flow on the stand-in device)."""
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+    from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
+    from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager
+
+    class IO(glue.HierarchicalCheckpointIO):
+        def to_tensor_aware_state_dict(self, checkpoint):
+            return BasicTensorAwareStateDict(checkpoint)
+
+        def from_tensor_aware_state_dict(self, tasd, **kw):
+            return tasd.state_dict
+
+    class GlobalIO:
+        def load_checkpoint(self, path, map_location=None, **kw):
+            return {"from": "global"}
+
+        def save_checkpoint(self, *a, **k):
+            raise AssertionError("a local save must not reach the global CheckpointIO")
+
+    with fake_device(monkeypatch) as (engine, lib):
+        mgr = LocalCheckpointManager(shm_dir / "ptl")
+        io = IO(GlobalIO(), mgr, get_global_ckpt_iteration_fn=lambda p: int(str(p).rsplit("=", 1)[-1]), async_save=True)
+        q = AsyncCallsQueue(persistent=False)
+        g = torch.Generator().manual_seed(21)
+        state = {f"param_{i}": FakeCudaTensor.wrap(torch.rand(513, 255, generator=g)) for i in range(6)}
+        want = {k: plain(v).clone() for k, v in state.items()}
+
+        class Trainer:
+            global_step = 40
+
+            def save_checkpoint(self, path, storage_options=None):
+                req = io.save_checkpoint({"state_dict": dict(state), "global_step": self.global_step}, path, storage_options)
+                q.schedule_async_request(req)
+
+        try:
+            cb = glue.LocalCheckpointCallback(every_n_train_steps=20)
+            cb._save_last_checkpoint(Trainer(), {})
+            q.maybe_finalize_async_calls(blocking=True, no_dist=False)
+            assert io.load_checkpoint("/global/step=50") == {"from": "global"}
+            io2 = IO(GlobalIO(), LocalCheckpointManager(shm_dir / "ptl"), get_global_ckpt_iteration_fn=lambda p: 30)
+            resumed = io2.load_checkpoint("/global/step=30")
+            assert resumed["global_step"] == 40
+            assert all(resumed["state_dict"][k].is_cuda and torch.equal(plain(resumed["state_dict"][k]), w) for k, w in want.items())
+        finally:
+            q.close()

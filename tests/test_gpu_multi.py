@@ -71,7 +71,6 @@ def _w_allgather_batch(rank, world, mode):
             assert a.is_cuda and bit_equal(a, b)
 
 
-_UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="not yet validated on a B200")
 
 
 def _w_allgather_streamed_small_chunks(rank, world):
@@ -81,7 +80,6 @@ def _w_allgather_streamed_small_chunks(rank, world):
     _w_allgather_batch(rank, world, "stream")
 
 
-@_UNVALIDATED
 def test_all_gather_batch_streamed_exchange(built_library):
     """NVRX_B200_EXCHANGE=stream: pack on the training stream, chunked all-gather + drain in the background."""
     world = min(torch.cuda.device_count(), 8)
@@ -154,7 +152,6 @@ def _w_replicated_zero_copy(rank, world, root, jump, factor, kill):
     assert rank in kill or (mine and all(os.stat(p).st_nlink == 2 for p in mine)), [(str(p), os.stat(p).st_nlink) for p in mine]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("NVRX_B200_TEST_UNVALIDATED") != "1", reason="opt-in mode, not yet validated on a B200")
 def test_replicated_save_zero_copy_pairs(built_library, shm_dir):
     """Replicated zero-copy (written after round 1's GPU budget was spent): each member's slice of the exchange buffer is
     drained into a slot of its own in container geometry and published as that member's file."""
