@@ -619,11 +619,11 @@ def run_arm(args, rank, world, local):
             "tensors": len(tensors),
             "l2": "inputs (16 GB) >> L2 (126 MB); no flush needed",
             "scale": args.scale,
-            "path": ("nvidia_resiliency_ext...TorchAsyncCheckpoint.async_save (pack kernel on the training stream, side-stream drain, "
-                     "writer process follows the drain)" if engine_arm else
-                     "reference flow (oracle/reference_port.py): per-tensor pinned D2H + torch.cuda.synchronize() + fork + torch.save"
-                     + ("; the reference has no narrowing, it saves fp32" if args.narrow else "")),
-        },
+        },  # identical in both arms (the driver compares it); what differs between the arms is under "path" / "engine"
+        "path": ("nvidia_resiliency_ext...TorchAsyncCheckpoint.async_save (pack kernel on the training stream, side-stream drain, "
+                 "writer process follows the drain)" if engine_arm else
+                 "reference flow (oracle/reference_port.py): per-tensor pinned D2H + torch.cuda.synchronize() + fork + torch.save"
+                 + ("; the reference has no narrowing, it saves fp32" if args.narrow else "")),
         "e2e": {
             "value": round(world * total / safe_s / 1e9, 2),
             "unit": "GB/s",
@@ -654,8 +654,7 @@ def run_arm(args, rank, world, local):
         algo = plan.algorithmic_bytes
         achieved = algo / (kernel_ms * 1e-3) / 1e9
         traffic, traffic_src = (args.traffic_bytes, "command line") if args.traffic_bytes else ncu_traffic("pack LDG narrow" if args.narrow else "pack TMA")
-        line["config"]["packed_bytes_per_rank"] = plan.staging_bytes
-        line["config"]["walker"] = os.environ.get("NVRX_B200_VARIANT", "auto")
+        line["engine"] = {"packed_bytes_per_rank": plan.staging_bytes, "walker": os.environ.get("NVRX_B200_VARIANT", "auto")}
         line["roofline"] = {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,

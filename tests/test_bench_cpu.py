@@ -33,6 +33,7 @@ def bench(monkeypatch):
     monkeypatch.setattr(B, "min_over_ranks", lambda x: float(x))
     monkeypatch.setattr(torch.cuda, "Event", _Event)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None))
     return B
 
 
@@ -88,3 +89,44 @@ def test_workload_matches_the_survey():
     params = sum(int(torch.tensor(s).prod()) for _, s in shapes)
     assert len(shapes) == 291 and params == 1_003_782_656  # 1/8 row shard of Llama-3-8B
     assert set(B.WORKLOADS) == {"c2", "c3"} and "16.06 GB" in B.WORKLOADS["c2"]
+
+
+def _args(B, **over):
+    import argparse
+
+    ns = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="engine", config="c2", narrow=False, persist_steps=1, load_reps=1, scale=1.0,
+                            baseline_sample_gb=0.001, no_cpu_baseline=True, no_verify=False, no_restore=False, no_training_loop=True,
+                            no_ceiling=True, traffic_bytes=None)
+    for k, v in over.items():
+        setattr(ns, k, v)
+    return ns
+
+
+def test_run_arm_assembles_the_same_config_in_both_arms(bench, monkeypatch, built_library, dist_1rank):
+    """The whole of run_arm (minus the GEMM loop and the PCIe ceiling, which need a GPU) on the stand-in device: the JSON line
+    of both arms is assembled without error, carries the contract's keys, and `config` is identical in both (the driver
+    compares it to decide whether the two arms measured the same thing)."""
+    import json
+
+    B = bench
+    monkeypatch.setattr(B, "ClockSampler", lambda idx: types.SimpleNamespace(__enter__=lambda: None, __exit__=lambda *a: None, summary=lambda: {"sm_mhz": None}))
+    with fake_device(monkeypatch) as (engine, lib):
+        def state(dev, seed=0, scale=1.0):
+            sd = _small_state()
+            return sd, sum(t.numel() * t.element_size() for t in B.flatten(sd))
+
+        monkeypatch.setattr(B, "llama3_8b_shard_state", state)
+        eng = B.run_arm(_args(B), 0, 1, 0)
+        c3 = B.run_arm(_args(B, config="c3", narrow=True, no_restore=True), 0, 1, 0)
+    monkeypatch.setattr(B, "llama3_8b_shard_state", lambda dev, seed=0, scale=1.0: (_small_state(False), sum(t.numel() * t.element_size() for t in B.flatten(_small_state(False)))))
+    ref = B.run_arm(_args(B, impl="reference", no_restore=True), 0, 1, 0)
+    for line in (eng, c3, ref):
+        json.dumps(line)
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                    "data", "config", "e2e", "gpu_launches", "stall_ms", "impl", "clocks"):
+            assert key in line, key
+        assert line["ms_per_step"] > 0 and line["value"] >= 0 and line["e2e"]["value"] >= 0 and line["verify"] == "bit-exact"  # (KB-sized state)
+    assert eng["config"] == ref["config"] and eng["config"]["workload"] == B.WORKLOADS["c2"]
+    assert eng["impl"] == "engine" and ref["impl"] == "reference" and ref["gpu_launches"] == 0 and eng["gpu_launches"] > 0
+    assert eng["roofline"]["bound"] == "hbm" and eng["roofline"]["algorithmic_bytes_per_launch"] > 0 and "roofline" not in ref and "cpu_baseline" in ref
+    assert eng["restore_verify"] == "bit-exact" and c3["config"]["workload"] == B.WORKLOADS["c3"] and c3["dtype"].startswith("f32->bf16")
