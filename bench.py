@@ -462,10 +462,16 @@ def local_manager_leg(arm_name, sd, tensors, total, rank, narrow):
             q = AsyncCallsQueue(persistent=False)
             # like TorchAsyncCheckpoint.warmup(): staging and host slot for THIS state exist before the timed save (the async
             # loop above may have run on narrowed, i.e. smaller, snapshots; the reference arm's pinned cache is warm from its loop)
+            from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+
             eng = SnapshotEngine.get()
-            need = sum(t.numel() * t.element_size() for t in tensors) + (len(tensors) + 8) * 4096
+            # exactly what save() will ask for (container geometry + room for the container's tail): a slot the async loop left
+            # qualifies as it is; only a loop that ran on narrowed (half-size) snapshots makes this create one, untimed
+            sizes = [t.numel() * t.element_size() for t in tensors]
+            span = ptzip.slot_offsets(sizes)[1]
+            need = -(-span // 512) * 512 + ptzip.slot_tail_room(len(sizes))
             eng._ensure_staging(need)
-            eng._release(eng._acquire_slot(need))  # one free slot that is large enough (a no-op when the async loop left one)
+            eng._release(eng._acquire_slot(need))
             tasd = BasicTensorAwareStateDict(fresh_containers(sd))
             torch.cuda.synchronize()
             dist.barrier()
