@@ -291,7 +291,8 @@ def finish_crcs(offsets: Sequence[int], nbytes: Sequence[int], values_ptr: int, 
 
 def gpu_crc_enabled() -> bool:
     """Opt-in (``NVRX_B200_GPU_CRC=1``): record checksums of checkpoint files come from a kernel over the staging buffer
-    instead of being left zero (or summed by CPU threads with ``NVRX_B200_ZIP_CRC=1``)."""
+    instead of from the writer's CPU threads (the default: ``nvrx_hostbuf_crc32v``, PCLMULQDQ folding; ``NVRX_B200_ZIP_CRC=0``
+    leaves them zero)."""
     return os.environ.get("NVRX_B200_GPU_CRC", "0") == "1"
 
 
