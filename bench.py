@@ -17,7 +17,8 @@ the product's ``TorchAsyncCheckpoint`` or the port of the reference's ``TorchAsy
   value       state bytes of all ranks / STALL: the wall time ``async_save`` keeps the training stream blocked (from the
               call until an event recorded on the training stream right after it has completed).  The state is resident
               in HBM when the timed region starts; this is the "snapshot GB/s" a training loop sees.  ms_per_step = that
-              stall (mean of the K steps, max over ranks).
+              stall (mean of the K steps, max over ranks).  stall_device_ms = the same span timed on the device (CUDA events
+              recorded on the training stream right before and after the call).
   e2e         same metric until the snapshot bytes are SAFE IN HOST MEMORY (the D2H of the whole snapshot is inside the
               timed region): PCIe-bound in both arms.
   stall_beside_training_ms   the same stall measured inside a running GEMM loop: extra wall time of a window of
@@ -300,18 +301,24 @@ class ReferenceArm:
 def api_loop(arm, sd, path, steps, warmup, persist_steps, trace_rows=None):
     """K checkpoints through ``arm``; per step: stall, time to host-safe, time to persisted (only when the step wrote)."""
     ev = torch.cuda.Event()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stall, safe, persist = [], [], []
+    api_loop.device_ms = []  # the same stall as the DEVICE saw it: CUDA events around the call on the training stream
     for it in range(warmup + steps):
         write = arm.writes_every_step or it >= warmup + steps - persist_steps
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        ev0.record()
         arm.save(sd, path, write)
         t_ret = time.perf_counter()
+        ev1.record()
         ev.record()
         ev.synchronize()  # the training stream is free again here
         t1 = time.perf_counter()
+        if it >= warmup:
+            api_loop.device_ms.append(ev0.elapsed_time(ev1))
         if it >= warmup and trace_rows is not None:
             tr = arm.trace()
             if tr:
@@ -640,6 +647,7 @@ def run_arm(args, rank, world, local):
             "d2h_ceiling": ceiling,
         },
         "stall_ms": round(stall_s * 1e3, 3),
+        "stall_device_ms": round(max_over_ranks(mean(api_loop.device_ms)), 3) if getattr(api_loop, "device_ms", None) else None,
         "stall_beside_training_ms": None if load_ms is None else round(load_ms, 3),
         "training_window_ms": None if base_ms is None else round(base_ms, 1),
         "persist_s": None if persist_s is None else round(persist_s, 3),

@@ -23,6 +23,9 @@ class _Event:
     def synchronize(self):
         pass
 
+    def elapsed_time(self, other):
+        return 1.0
+
 
 @pytest.fixture
 def bench(monkeypatch):
