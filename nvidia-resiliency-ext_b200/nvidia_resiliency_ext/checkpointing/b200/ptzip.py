@@ -384,45 +384,68 @@ def slot_is_published(slot_path: str) -> bool:
         return False
 
 
+def _mapping_base(path, ptr: int) -> Optional[int]:
+    """Address at which offset 0 of ``path`` is mapped in this process, taken from the mapping that contains ``ptr``
+    (``/proc/self/maps``); None when no mapping of that file contains it."""
+    try:
+        real = os.path.realpath(os.fspath(path))
+        st = os.stat(real)
+        with open("/proc/self/maps") as f:
+            for line in f:
+                parts = line.split(None, 5)
+                if len(parts) < 6:
+                    continue
+                lo, hi = (int(x, 16) for x in parts[0].split("-"))
+                if not lo <= ptr < hi:
+                    continue
+                name = parts[5].rstrip("\n")
+                if name.endswith(" (deleted)"):
+                    name = name[: -len(" (deleted)")]
+                try:
+                    same = name == real or os.path.samestat(os.stat(name), st)
+                except OSError:
+                    same = False
+                return lo - int(parts[2], 16) if same else None
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def tensor_offsets_in_file(path, tensors: Sequence[torch.Tensor]) -> Optional[List[int]]:
     """File offsets of the data of ``tensors`` -- tensors ``torch.load(path, mmap=True)`` returned, in ascending file order --
     or None when they are not views of the data records of one mapping of that file, ascending and 16-byte aligned.
 
-    The usual case is one record per tensor in order (``data/i`` is tensor i); objects that pickle other storages first (a host
-    tensor in the ``common`` part of a Megatron-style state dict) shift the numbering, so the general rule is: there is ONE
-    base address such that every tensor starts at ``base + offset of some data record`` that is large enough."""
+    The address the file is mapped at comes from ``/proc/self/maps`` (exact).  Every tensor must then start at the data offset
+    of a ``data/<k>`` record that is large enough: usually record i for tensor i, but objects that pickle other storages first
+    (a host tensor in the ``common`` part of a Megatron-style state dict) shift the numbering.  Without a usable maps entry the
+    base is inferred from the records (tensor i = record i, else the one base under which every tensor hits a record)."""
     live = [(i, t) for i, t in enumerate(tensors) if t.numel()]
     if not live or any(t.is_cuda or not t.is_contiguous() for _, t in live):
         return None
     try:
         reader = torch._C.PyTorchFileReader(os.fspath(path))
+        recs = {}
+        for name in reader.get_all_records():
+            if name.startswith("data/"):
+                recs[reader.get_record_offset(name)] = name
         first_i, first_t = live[0]
-        base = None
-        if reader.has_record(f"data/{first_i}"):
-            guess = first_t.data_ptr() - reader.get_record_offset(f"data/{first_i}")  # address the file is mapped at
-            if all(reader.has_record(f"data/{i}") and reader.get_record_offset(f"data/{i}") == t.data_ptr() - guess for i, t in live):
+
+        def fits(guess: int) -> bool:
+            return all((t.data_ptr() - guess) in recs for _, t in live)
+
+        base = _mapping_base(path, first_t.data_ptr())
+        if base is not None and not fits(base):
+            return None
+        if base is None and reader.has_record(f"data/{first_i}"):
+            guess = first_t.data_ptr() - reader.get_record_offset(f"data/{first_i}")
+            if len(live) > 1 and all(reader.has_record(f"data/{i}") and reader.get_record_offset(f"data/{i}") == t.data_ptr() - guess for i, t in live):
                 base = guess
         if base is None:
-            recs = {}
-            for name in reader.get_all_records():
-                if name.startswith("data/"):
-                    recs[reader.get_record_offset(name)] = reader.get_record_size(name) if hasattr(reader, "get_record_size") else None
-            need = first_t.numel() * first_t.element_size()
-            for off0, size0 in sorted(recs.items()):
-                if size0 is not None and size0 < need:
-                    continue
-                guess = first_t.data_ptr() - off0
-                ok = True
-                for _, t in live:
-                    size = recs.get(t.data_ptr() - guess, -1)
-                    if size == -1 or (size is not None and size < t.numel() * t.element_size()):
-                        ok = False
-                        break
-                if ok:
-                    base = guess
-                    break
-            if base is None:
-                return None
+            candidates = [first_t.data_ptr() - off0 for off0 in sorted(recs)]
+            good = [g for g in candidates if g % 4096 == 0 and fits(g)]
+            if len(good) != 1:
+                return None  # ambiguous or impossible: let the caller take the path that does not need file offsets
+            base = good[0]
     except (RuntimeError, OSError):
         return None
     offs, end = [], 0

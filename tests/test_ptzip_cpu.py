@@ -159,3 +159,31 @@ def test_patch_record_crcs_also_in_zip64_containers(tmp_path):
         by_name = {zi.filename.split("/", 1)[1]: zi for zi in z.infolist()}
         assert by_name["data/0"].CRC == 0x11223344 and by_name["data/1"].CRC == 0x55667788
         assert by_name["data/1"].header_offset > 4 * 1024**3
+
+
+def test_mapping_base_is_read_from_proc_maps(tmp_path):
+    """tensor_offsets_in_file takes the address a checkpoint is mapped at from /proc/self/maps (exact), also through a second
+    name of the same file (a hard link, as the zero-copy publish creates) and for a single tensor behind another storage --
+    the case where inferring the base from the records alone is ambiguous."""
+    import os
+
+    import torch
+
+    from nvidia_resiliency_ext.checkpointing.b200 import ptzip
+
+    obj = {"common": {"rng": torch.arange(40, dtype=torch.int64)}, "payload": [torch.arange(80, dtype=torch.int32)]}
+    path = tmp_path / "one.pt"
+    torch.save(obj, path)
+    link = tmp_path / "other_name.pt"
+    os.link(path, link)
+    loaded = torch.load(path, mmap=True)
+    t = loaded["payload"][0]
+    reader = torch._C.PyTorchFileReader(str(path))
+    want = reader.get_record_offset("data/1")  # data/0 is the host tensor pickled first
+    base = ptzip._mapping_base(path, t.data_ptr())
+    assert base is not None and t.data_ptr() - base == want and base % 4096 == 0
+    assert ptzip._mapping_base(link, t.data_ptr()) == base  # same inode under another name
+    assert ptzip.tensor_offsets_in_file(path, [t]) == [want]
+    assert ptzip.tensor_offsets_in_file(link, [t]) == [want]
+    assert ptzip._mapping_base(path, torch.zeros(4).data_ptr()) is None  # a pointer that is not in a mapping of the file
+    assert ptzip.tensor_offsets_in_file(path, [torch.zeros(4)]) is None
