@@ -582,3 +582,39 @@ def test_ptl_glue_drives_the_local_manager(glue, monkeypatch, built_library, shm
             assert all(resumed["state_dict"][k].is_cuda and torch.equal(plain(resumed["state_dict"][k]), w) for k, w in want.items())
         finally:
             q.close()
+
+
+def test_restore_of_arbitrary_mixes_of_slot_views_and_host_tensors(monkeypatch, built_library, dist_1rank):
+    """engine.restore must give every tensor back whatever mix it is handed: views of a slot in order (read in place), in any
+    other order or only some of them (taken out of the slot first), views of two different slots, plain host tensors."""
+    import random
+
+    with fake_device(monkeypatch) as (engine, lib):
+        rng = random.Random(7)
+        for trial in range(25):
+            a = [FakeCudaTensor.wrap(torch.randn(rng.choice([1, 7, 64, 513, 4097]), generator=torch.Generator().manual_seed(trial * 10 + i))) for i in range(rng.randint(1, 6))]
+            b = [FakeCudaTensor.wrap(torch.randn(rng.choice([3, 100, 2048]), generator=torch.Generator().manual_seed(trial * 10 + 50 + i))) for i in range(rng.randint(1, 4))]
+            sa, sb = engine.snapshot(a), engine.snapshot(b)
+            sa.wait(), sb.wait()
+            pool = [(v, plain(t).clone()) for v, t in zip(sa.host_views(), a)] + [(v, plain(t).clone()) for v, t in zip(sb.host_views(), b)]
+            pool += [(torch.full((rng.randint(1, 300),), float(trial)), None)]
+            mode = trial % 5
+            if mode == 0:
+                pick = pool[: len(a)]  # one slot, in order -> in place
+            elif mode == 1:
+                pick = list(reversed(pool[: len(a)]))
+            elif mode == 2:
+                pick = rng.sample(pool, rng.randint(1, len(pool)))
+            elif mode == 3:
+                pick = pool[len(a) : len(a) + len(b)] + pool[: len(a)]  # two slots
+            else:
+                pick = [pool[-1]] + pool[: len(a)]  # a plain host tensor in front of slot views
+            if rng.random() < 0.5:
+                sa.release(), sb.release()  # the slots may be handed out again by the restore itself
+            got = engine.restore([v for v, _ in pick])
+            for g, (v, want) in zip(got, pick):
+                want = want if want is not None else v
+                assert g.is_cuda and torch.equal(plain(g), plain(want)), (trial, mode)
+            if not sa.released:
+                sa.release(), sb.release()
+            assert not any(s.busy for s in engine._slots)
