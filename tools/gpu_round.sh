@@ -35,19 +35,19 @@ if [[ $WHAT == all || $WHAT == bench ]]; then
   guarded timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 fi
 if [[ $WHAT == zerocopy ]]; then
-  # opt-in modes written without GPU time in round 1: zero-copy persistence and the DCP async writer.  Validate, then measure.
-  NVRX_B200_TEST_UNVALIDATED=1 guarded timeout 900 python -m pytest tests/test_gpu_zcrc.py tests/test_gpu_zzero_copy.py tests/test_gpu_zdcp.py -m gpu -q --timeout=600 > gpurun_out/pytest_zerocopy.log 2>&1
+  # zero-copy persistence (default since round 2), GPU checksums (opt-in), DCP async writer: tests, then the bench in each writer mode
+  guarded timeout 900 python -m pytest tests/test_gpu_zcrc.py tests/test_gpu_zzero_copy.py tests/test_gpu_zdcp.py -m gpu -q --timeout=600 > gpurun_out/pytest_zerocopy.log 2>&1
   tail -25 gpurun_out/pytest_zerocopy.log
   guarded timeout 600 python tools/crc_bench.py --gb 2 > gpurun_out/crc_bench.jsonl 2> gpurun_out/crc_bench.err
   guarded timeout 600 python tools/crc_bench.py --gb 16 >> gpurun_out/crc_bench.jsonl 2>> gpurun_out/crc_bench.err; cat gpurun_out/crc_bench.jsonl
-  guarded timeout 900 python bench.py > gpurun_out/bench_copy.json 2> gpurun_out/bench_copy.err; cat gpurun_out/bench_copy.json
-  NVRX_B200_WRITE_FALLOCATE=1 guarded timeout 900 python bench.py > gpurun_out/bench_fallocate.json 2> gpurun_out/bench_fallocate.err; cat gpurun_out/bench_fallocate.json
-  NVRX_B200_RESTORE_PREAD=1 guarded timeout 900 python bench.py > gpurun_out/bench_pread.json 2> gpurun_out/bench_pread.err; cat gpurun_out/bench_pread.json
-  NVRX_B200_ZERO_COPY=1 NVRX_B200_GPU_CRC=1 guarded timeout 900 python bench.py > gpurun_out/bench_zerocopy.json 2> gpurun_out/bench_zerocopy.err; tail -3 gpurun_out/bench_zerocopy.err; cat gpurun_out/bench_zerocopy.json
+  NVRX_B200_ZERO_COPY=0 guarded timeout 900 python bench.py > gpurun_out/bench_copy.json 2> gpurun_out/bench_copy.err; cat gpurun_out/bench_copy.json
+  NVRX_B200_ZERO_COPY=0 NVRX_B200_NO_FALLOCATE=1 guarded timeout 900 python bench.py > gpurun_out/bench_copy_nofallocate.json 2> gpurun_out/bench_copy_nofallocate.err; cat gpurun_out/bench_copy_nofallocate.json
+  NVRX_B200_RESTORE_PREAD=0 guarded timeout 900 python bench.py > gpurun_out/bench_mmap_restore.json 2> gpurun_out/bench_mmap_restore.err; cat gpurun_out/bench_mmap_restore.json
+  NVRX_B200_GPU_CRC=1 guarded timeout 900 python bench.py > gpurun_out/bench_zerocopy.json 2> gpurun_out/bench_zerocopy.err; tail -3 gpurun_out/bench_zerocopy.err; cat gpurun_out/bench_zerocopy.json
 fi
 if [[ $WHAT == multizc ]]; then
   # 2+ GPUs: the whole multi-GPU suite including the gated replicated zero-copy test
-  NVRX_B200_TEST_UNVALIDATED=1 guarded timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi_zc.log 2>&1
+  guarded timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --durations=10 --timeout=900 > gpurun_out/pytest_multi_zc.log 2>&1
   tail -30 gpurun_out/pytest_multi_zc.log
 fi
 if [[ $WHAT == multi ]]; then
