@@ -91,12 +91,12 @@ def test_torch_async_checkpoint_zero_copy(monkeypatch, built_library, shm_dir, d
                 ckpt.finalize_async_save(blocking=True)
                 assert os.stat(path).st_nlink == 2, "hard link to the slot expected"
                 _same(torch.load(path, weights_only=False), want)
-                if gpu_crc == "1":
-                    with zipfile.ZipFile(path) as zf:
-                        for n in zf.namelist():
-                            if not n.endswith("/.pad"):
-                                zf.read(n)  # CRC check
-                        assert zf.getinfo("archive/data/0").CRC == zlib.crc32(want["model"]["w"].numpy().tobytes())
+                # record checksums are valid whoever computed them: the GPU kernel (opt-in) or the writer's threads (default)
+                with zipfile.ZipFile(path) as zf:
+                    for n in zf.namelist():
+                        if not n.endswith("/.pad"):
+                            zf.read(n)  # CRC check
+                    assert zf.getinfo("archive/data/0").CRC == zlib.crc32(want["model"]["w"].numpy().tobytes())
                 if i >= 1:
                     _same(torch.load(paths[i - 1], weights_only=False), _state(i - 1, wrap=False))  # not overwritten
                     os.unlink(paths[i - 1])
