@@ -298,12 +298,12 @@ class ReferenceArm:
         self.ckpt.finalize(blocking=True)
 
 
-def api_loop(arm, sd, path, steps, warmup, persist_steps, trace_rows=None):
+def api_loop(arm, sd, path, steps, warmup, persist_steps, trace_rows=None, device_ms=None):
     """K checkpoints through ``arm``; per step: stall, time to host-safe, time to persisted (only when the step wrote)."""
     ev = torch.cuda.Event()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stall, safe, persist = [], [], []
-    api_loop.device_ms = []  # the same stall as the DEVICE saw it: CUDA events around the call on the training stream
+    # ``device_ms`` (a list to fill): the same stall as the DEVICE saw it, CUDA events around the call on the training stream
     for it in range(warmup + steps):
         write = arm.writes_every_step or it >= warmup + steps - persist_steps
         torch.cuda.synchronize()
@@ -317,8 +317,8 @@ def api_loop(arm, sd, path, steps, warmup, persist_steps, trace_rows=None):
         ev.record()
         ev.synchronize()  # the training stream is free again here
         t1 = time.perf_counter()
-        if it >= warmup:
-            api_loop.device_ms.append(ev0.elapsed_time(ev1))
+        if it >= warmup and device_ms is not None:
+            device_ms.append(ev0.elapsed_time(ev1))
         if it >= warmup and trace_rows is not None:
             tr = arm.trace()
             if tr:
@@ -578,7 +578,8 @@ def run_arm(args, rank, world, local):
     out_dir = shm_dir(rank)
     path = out_dir / "ckpt.pt"  # one file per rank, overwritten every step
     trace_rows = [] if os.environ.get("NVRX_B200_TRACE", "0") == "1" else None
-    stall, safe, persist = api_loop(arm, sd, path, args.steps, args.warmup, args.persist_steps, trace_rows)
+    device_ms = []
+    stall, safe, persist = api_loop(arm, sd, path, args.steps, args.warmup, args.persist_steps, trace_rows, device_ms)
     clocks.__exit__(None, None, None)
     stall_s = max_over_ranks(mean(stall))  # the K timed steps, mean -> ms_per_step
     safe_s = max_over_ranks(mean(safe))
@@ -647,7 +648,7 @@ def run_arm(args, rank, world, local):
             "d2h_ceiling": ceiling,
         },
         "stall_ms": round(stall_s * 1e3, 3),
-        "stall_device_ms": round(max_over_ranks(mean(api_loop.device_ms)), 3) if getattr(api_loop, "device_ms", None) else None,
+        "stall_device_ms": round(max_over_ranks(mean(device_ms)), 3) if device_ms else None,
         "stall_beside_training_ms": None if load_ms is None else round(load_ms, 3),
         "training_window_ms": None if base_ms is None else round(base_ms, 1),
         "persist_s": None if persist_s is None else round(persist_s, 3),

@@ -125,7 +125,7 @@ def test_run_arm_assembles_the_same_config_in_both_arms(bench, monkeypatch, buil
     ref = B.run_arm(_args(B, impl="reference", no_restore=True), 0, 1, 0)
     for line in (eng, c3, ref):
         json.dumps(line)
-        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "stall_device_ms",
                     "data", "config", "e2e", "gpu_launches", "stall_ms", "impl", "clocks"):
             assert key in line, key
         assert line["ms_per_step"] > 0 and line["value"] >= 0 and line["e2e"]["value"] >= 0 and line["verify"] == "bit-exact"  # (KB-sized state)
