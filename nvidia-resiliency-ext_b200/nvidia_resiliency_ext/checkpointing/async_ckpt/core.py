@@ -598,11 +598,6 @@ class AsyncCallsQueue(metaclass=ObjectTracker):
             # requests built against an older AsyncRequest definition
             async_request = AsyncRequest(**async_request._asdict())
         async_request = async_request.freeze()
-        for fn in async_request.finalize_fns:
-            try:
-                fn.scheduled_by_queue = True  # lets the owner of pinned snapshot slots tell "aborted" from "not scheduled yet"
-            except AttributeError:
-                pass
         # finalize functions stay on the trainer: they are closures over managers / process groups
         caller.schedule_async_call(async_request._replace(call_idx=self.call_idx, finalize_fns=[]))
         self.async_calls.append(_ActiveAsyncRequest(self.call_idx, caller, async_request))

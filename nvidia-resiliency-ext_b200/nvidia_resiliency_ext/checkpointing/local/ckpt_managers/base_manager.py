@@ -60,7 +60,7 @@ class BaseCheckpointManager(ABC):
         self.repl_strategy = repl_strategy
         self.session_id = session_id
         self._rank = None
-        self._outstanding = []  # (AsyncRequest, [Snapshot]) of saves that were handed out and not finalized yet
+        self._outstanding = []  # (weak reference to the save's finalize_fn, [Snapshot]) of saves not finalized yet
 
     @property
     def rank(self):
@@ -304,7 +304,7 @@ class BaseCheckpointManager(ABC):
                     s.wait()
         if is_async:
             request = AsyncRequest(self._save_fn, (to_save, descs), [finalize_fn], async_fn_kwargs={})
-            self._outstanding.append((request, snaps))
+            self._track(request, snaps)
             return request
 
         try:
@@ -317,41 +317,25 @@ class BaseCheckpointManager(ABC):
             torch.distributed.barrier()
         finalize_fn()
 
-    def _reap_abandoned(self):
-        """Give back the host slots of earlier asynchronous saves that will never be finalized.
+    def _track(self, request: AsyncRequest, snaps) -> None:
+        """Remember the host slots of an asynchronous save until its ``finalize_fn`` has run -- or can never run any more.
 
-        ``finalize_fn`` releases the slots of a save.  A save whose queue was aborted (``abort_nvrx_checkpoint`` -- the
-        in-process restart path, reference ``inprocess/abort.py:201``) or closed never runs it, and each such save would pin one
-        or two snapshot-sized shm slots for good.  A request is *abandoned* when no live ``AsyncCallsQueue`` holds it any more
-        and its slots are still busy; requests the caller has not scheduled yet (or runs with ``execute_sync``) are kept as long
-        as the caller keeps the request object alive."""
-        if not self._outstanding:
-            return
-        import sys
+        ``finalize_fn`` releases the slots.  A save whose queue was aborted (``abort_nvrx_checkpoint`` -- the in-process restart
+        path, reference ``inprocess/abort.py:201``) or whose request the caller dropped never runs it, and each such save would pin
+        one or two snapshot-sized shm slots for good.  The request is the only owner of its ``finalize_fn``: when the queue and
+        the caller have let go of the request, the function object dies, and that is the moment the slots go back (releasing is
+        idempotent, so the normal path is unaffected)."""
+        import weakref
 
-        from ...async_ckpt.core import AsyncCallsQueue
-
-        scheduled = set()
-        for queue in AsyncCallsQueue.get_instances():
-            for active in list(getattr(queue, "async_calls", ())):
-                for fn in getattr(getattr(active, "async_request", None), "finalize_fns", ()) or ():
-                    scheduled.add(id(fn))
-        keep = []
-        for request, snaps in self._outstanding:
-            if all(s.released for s in snaps):
-                continue  # finalized
-            held_by_queue = any(id(fn) in scheduled for fn in request.finalize_fns)
-            was_scheduled = any(getattr(fn, "scheduled_by_queue", False) for fn in request.finalize_fns)
-            # not scheduled yet: the caller may still do so while it holds the request (references: the tuple in
-            # self._outstanding, the loop variable, getrefcount's argument)
-            pending_at_caller = not was_scheduled and sys.getrefcount(request) > 3
-            if held_by_queue or pending_at_caller:
-                keep.append((request, snaps))
-                continue
-            logger.warning("local checkpoint save was never finalized (aborted queue?): releasing its host snapshot slots")
+        def give_back(_ref, snaps=tuple(snaps)):
             for s in snaps:
                 s.release()
-        self._outstanding = keep
+
+        self._outstanding.append((weakref.ref(request.finalize_fns[0], give_back), snaps))
+
+    def _reap_abandoned(self):
+        """Forget the saves that are done with their slots (finalized, or abandoned and given back by :meth:`_track`)."""
+        self._outstanding = [(ref, snaps) for ref, snaps in self._outstanding if not all(s.released for s in snaps)]
 
     def release_unfinalized(self):
         """Release the host slots of every save of this manager that has not been finalized (call after aborting the queue,

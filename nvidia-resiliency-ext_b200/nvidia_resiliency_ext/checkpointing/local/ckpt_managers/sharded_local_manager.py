@@ -187,7 +187,7 @@ class ShardedLocalCheckpointManager(LocalCheckpointManager):
         args = ({my_id: state_dict}, descs, frag_specs)
         if is_async:
             request = AsyncRequest(self._save_sharded_fn, args, [finalize_fn], async_fn_kwargs={})
-            self._outstanding.append((request, snaps))
+            self._track(request, snaps)
             return request
         try:
             self._save_sharded_fn(*args)
