@@ -44,7 +44,7 @@ def check_abi_calls() -> list:
 
     lib = _cabi.lib()
     problems = []
-    for path in list((ROOT / "nvidia-resiliency-ext_b200" / "nvidia_resiliency_ext").rglob("*.py")) + [ROOT / "bench.py", ROOT / "__graft_entry__.py"] + list((ROOT / "tools").glob("*.py")):
+    for path in list((ROOT / "nvidia-resiliency-ext_b200" / "nvidia_resiliency_ext").rglob("*.py")) + [ROOT / "bench.py", ROOT / "bench_c4.py", ROOT / "__graft_entry__.py"] + list((ROOT / "tools").glob("*.py")):
         tree = ast.parse(path.read_text())
         for node in ast.walk(tree):
             if isinstance(node, ast.Attribute) and node.attr.startswith("nvrx_") and node.attr not in _cabi.EXPORTED_SYMBOLS and node.attr != "nvrx_drain_aware":
@@ -61,7 +61,8 @@ def main():
 
     problems = []
     mods = [m.name for m in pkgutil.walk_packages(nvidia_resiliency_ext.__path__, "nvidia_resiliency_ext.")]
-    for name in mods + ["bench", "__graft_entry__"]:
+    extra = ["bench", "bench_c4", "__graft_entry__", "oracle.snapshot_oracle", "oracle.reference_port"]
+    for name in mods + extra:
         try:
             mod = importlib.import_module(name)
         except Exception as exc:  # noqa: BLE001 - optional dependencies (lightning)
@@ -69,7 +70,7 @@ def main():
             continue
         problems += check_module(mod)
     problems += check_abi_calls()
-    print("\n".join(problems) if problems else f"{len(mods) + 2} modules: no undefined globals, C-ABI calls match their signatures")
+    print("\n".join(problems) if problems else f"{len(mods) + len(extra)} modules: no undefined globals, C-ABI calls match their signatures")
     return 1 if problems else 0
 
 
