@@ -69,6 +69,18 @@ def main():
             print(f"skip {name}: {type(exc).__name__}: {exc}")
             continue
         problems += check_module(mod)
+    # GPU-only measurement tools that only define functions at import time
+    from importlib import util as _util
+
+    for tool in ("d2h_ceiling", "restore_breakdown", "overlap_timeline", "bench_replicate", "ncu_summary"):
+        spec = _util.spec_from_file_location(f"tools_{tool}", ROOT / "tools" / f"{tool}.py")
+        mod = _util.module_from_spec(spec)
+        try:
+            spec.loader.exec_module(mod)
+        except Exception as exc:  # noqa: BLE001
+            problems.append(f"tools/{tool}.py does not import: {type(exc).__name__}: {exc}")
+            continue
+        problems += check_module(mod)
     problems += check_abi_calls()
     print("\n".join(problems) if problems else f"{len(mods) + len(extra)} modules: no undefined globals, C-ABI calls match their signatures")
     return 1 if problems else 0
