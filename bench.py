@@ -569,9 +569,28 @@ def run_arm(args, rank, world, local):
     launches = 0
     engine = plan = None
     kernel_ms = None
+    c3_kernel = None
     if engine_arm:
         engine, plan, kernel_ms = kernel_leg(args, tensors, local)
         launches += args.steps
+        if not args.narrow and not args.no_c3_kernel:
+            # config C3's kernel in the same line (the driver only runs the default config): the narrowing pack alone, same timing
+            try:
+                import copy
+
+                a3 = copy.copy(args)
+                a3.narrow = True
+                _, plan3, ms3 = kernel_leg(a3, tensors, local)
+                peak3, _ = hbm_peak()
+                c3_kernel = {
+                    "kernel": "nvrx::walk_ldg<pack> (fp32->bf16 narrow)", "kernel_ms": round(ms3, 4),
+                    "algorithmic_bytes_per_launch": plan3.algorithmic_bytes, "achieved": round(plan3.algorithmic_bytes / (ms3 * 1e-3) / 1e9, 1),
+                    "peak": peak3, "unit": "GB/s", "frac": round(plan3.algorithmic_bytes / (ms3 * 1e-3) / 1e9 / peak3, 4),
+                    "packed_bytes_per_rank": plan3.staging_bytes, "timing": f"{args.steps} back-to-back launches, CUDA events, max over ranks",
+                }
+                launches += args.steps
+            except Exception as exc:  # noqa: BLE001 - an extra; must not take the C2 line with it
+                c3_kernel = {"error": repr(exc)}
         launches_before = engine.launches
 
     arm = (EngineArm if engine_arm else ReferenceArm)(args.narrow)
@@ -677,6 +696,8 @@ def run_arm(args, rank, world, local):
             "kernel_ms": round(kernel_ms, 4), "device_snapshot_GBps": round(world * total / (kernel_ms * 1e-3) / 1e9, 1),
             "timing": f"{args.steps} back-to-back launches of the whole-state pack, CUDA events on the launching stream, max over ranks",
         }
+        if c3_kernel is not None:
+            line["c3_kernel_roofline"] = c3_kernel
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sd, total, args.baseline_sample_gb)
     else:
@@ -736,6 +757,7 @@ def main():
     ap.add_argument("--no-restore", action="store_true")
     ap.add_argument("--no-training-loop", action="store_true")
     ap.add_argument("--no-ceiling", action="store_true")
+    ap.add_argument("--no-c3-kernel", action="store_true", help="skip the C3 (narrowing) kernel-only leg of the default run")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram read+write bytes per launch from the ncu capture")
     args, rest = ap.parse_known_args()
     if args.narrow:

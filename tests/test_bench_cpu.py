@@ -99,7 +99,7 @@ def _args(B, **over):
 
     ns = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="engine", config="c2", narrow=False, persist_steps=1, load_reps=1, scale=1.0,
                             baseline_sample_gb=0.001, no_cpu_baseline=True, no_verify=False, no_restore=False, no_training_loop=True,
-                            no_ceiling=True, traffic_bytes=None)
+                            no_ceiling=True, no_c3_kernel=False, traffic_bytes=None)
     for k, v in over.items():
         setattr(ns, k, v)
     return ns
@@ -132,4 +132,5 @@ def test_run_arm_assembles_the_same_config_in_both_arms(bench, monkeypatch, buil
     assert eng["config"] == ref["config"] and eng["config"]["workload"] == B.WORKLOADS["c2"]
     assert eng["impl"] == "engine" and ref["impl"] == "reference" and ref["gpu_launches"] == 0 and eng["gpu_launches"] > 0
     assert eng["roofline"]["bound"] == "hbm" and eng["roofline"]["algorithmic_bytes_per_launch"] > 0 and "roofline" not in ref and "cpu_baseline" in ref
+    assert "error" not in eng["c3_kernel_roofline"] and eng["c3_kernel_roofline"]["algorithmic_bytes_per_launch"] > 0 and "c3_kernel_roofline" not in c3
     assert eng["restore_verify"] == "bit-exact" and c3["config"]["workload"] == B.WORKLOADS["c3"] and c3["dtype"].startswith("f32->bf16")
