@@ -18,24 +18,63 @@ pytestmark = pytest.mark.gpu
 FIXTURES = Path(__file__).resolve().parent / "golden" / "ref_tests"
 
 
+def _kill_tagged(tag):
+    """Processes THIS run started (they inherited its unique environment tag) that outlived it, e.g. a checkpoint worker of an
+    aborted queue.  Exact pids, found by the tag, nothing else."""
+    import signal
+
+    for pid in [int(p) for p in os.listdir("/proc") if p.isdigit()]:
+        try:
+            env = open(f"/proc/{pid}/environ", "rb").read()
+        except OSError:
+            continue
+        if f"NVRX_REFSUITE_TAG={tag}".encode() in env.split(b"\0") and pid != os.getpid():
+            try:
+                os.kill(pid, signal.SIGKILL)
+            except OSError:
+                pass
+
+
 def run_reference_tests(files, world, extra=(), timeout=900, retries=0):
     """Run the given reference test files under torchrun against the mirror; returns pytest's stdout.  ``retries``: for groups
-    that contain wall-clock assertions of the reference (test_cleanup.py asserts finalize_fn < 30 ms on a shared box)."""
+    that contain wall-clock assertions of the reference (test_cleanup.py asserts finalize_fn < 30 ms on a shared box).
+    Output goes to files, not pipes: a process the tests leave behind would keep a pipe open and this call waiting for it."""
     for _ in range(retries):
         try:
             return run_reference_tests(files, world, extra, timeout, 0)
         except AssertionError:
             continue
+    import tempfile
+    import uuid
+
+    tag = uuid.uuid4().hex
     env = dict(os.environ)
     env["PYTHONPATH"] = str(PKG_ROOT)  # the mirror, and nothing of this repo's own tests/ or oracle/
+    env["NVRX_REFSUITE_TAG"] = tag
     env.pop("PYTEST_CURRENT_TEST", None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "--confcutdir", str(FIXTURES),
            "--rootdir", str(FIXTURES), *[f"tests/checkpointing/unit/{f}" for f in files], *extra]
-    res = subprocess.run(cmd, cwd=FIXTURES, env=env, capture_output=True, text=True, timeout=timeout)
-    tail = (res.stdout[-6000:] + "\n" + res.stderr[-3000:])
-    assert res.returncode == 0, tail
-    return res.stdout
+    with tempfile.TemporaryDirectory(prefix="nvrx_refsuite_") as tmp:
+        out_path, err_path = Path(tmp) / "stdout", Path(tmp) / "stderr"
+        code = None
+        try:
+            with open(out_path, "w") as so, open(err_path, "w") as se:
+                code = subprocess.run(cmd, cwd=FIXTURES, env=env, stdin=subprocess.DEVNULL, stdout=so, stderr=se, timeout=timeout).returncode
+        except subprocess.TimeoutExpired:
+            pass
+        finally:
+            _kill_tagged(tag)
+        stdout, stderr = out_path.read_text(errors="replace"), err_path.read_text(errors="replace")
+    tail = stdout[-6000:] + "\n" + stderr[-3000:]
+    assert code is not None, f"no result within {timeout} s\n{tail}"
+    assert code == 0, tail
+    return stdout
+
+
+def passed_count(out):
+    """N of pytest's closing ``N passed, ...`` line."""
+    return int(out.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
 
 
 def worlds():
@@ -76,5 +115,5 @@ def test_reference_dcp_async_writer_tests(world):
     for group in DCP_GROUPS:
         out = run_reference_tests(["test_async_writer.py"], world, ["-k", group], timeout=300, retries=1)
         assert " passed" in out and "failed" not in out, group
-        passed += int(out.rsplit(" passed", 1)[0].rsplit(None, 1)[-1])
+        passed += passed_count(out)
     assert passed == 13
