@@ -108,7 +108,10 @@ DCP_GROUPS = ["test_async_is_equivalent_to_sync", "test_invalid_async_setup", "t
 def test_reference_dcp_async_writer_tests(world):
     """All 13 cases of the reference's test_async_writer.py (the last -k pattern also selects ..._followed_by_delete).  Each
     group runs in a process of its own with its own time limit: in one process the file did not finish within 900 s on the
-    B200 box in round 2 (cause not found yet; every group passes on its own, profiles/r02_reference_dcp_tests.log)."""
+    B200 box in round 2 -- its last output came about 31 s in, then nothing.  Cause not found: every group passes on its own
+    (profiles/r02_reference_dcp_tests.log), and the same 13 scenarios replayed in ONE process on the stand-in device
+    (queues with daemon / non-daemon workers, failing writers, caches, abort + resume) finish, so the host logic alone does
+    not hang."""
     if world not in worlds():
         pytest.skip(f"needs >= {world} CUDA devices")
     passed = 0
