@@ -25,3 +25,18 @@ def test_the_product_never_imports_the_oracle_or_the_test_helpers():
         if re.search(r"^\s*(from|import)\s+(oracle|_fake_device|tests)\b", text, re.M) or re.search(r"#\s*include[^\n]*oracle", text):
             offenders.append(str(path))
     assert not offenders, offenders
+
+
+def test_every_environment_switch_is_documented():
+    """INTEGRATION.md's table is where users look: every NVRX_B200_* name the package or the C sources read must be in it
+    (families like NVRX_B200_*_CTAS_PER_SM count through their wildcard row)."""
+    import re
+
+    pkg = ROOT / "nvidia-resiliency-ext_b200"
+    names = set()
+    for path in [p for ext in ("*.py", "*.cu", "*.cuh", "*.h", "*.cpp") for p in pkg.rglob(ext)]:
+        names.update(re.findall(r"NVRX_B200_[A-Z0-9_]+", path.read_text()))
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    wildcards = [re.compile(re.escape(w).replace(r"\*", "[A-Z0-9_]+") + r"$") for w in re.findall(r"NVRX_B200_[A-Z0-9_*]*\*[A-Z0-9_*]*", doc)]
+    missing = sorted(n for n in names if n not in doc and not any(w.match(n) for w in wildcards))
+    assert not missing, missing
