@@ -134,3 +134,82 @@ def test_run_arm_assembles_the_same_config_in_both_arms(bench, monkeypatch, buil
     assert eng["roofline"]["bound"] == "hbm" and eng["roofline"]["algorithmic_bytes_per_launch"] > 0 and "roofline" not in ref and "cpu_baseline" in ref
     assert "error" not in eng["c3_kernel_roofline"] and eng["c3_kernel_roofline"]["algorithmic_bytes_per_launch"] > 0 and "c3_kernel_roofline" not in c3
     assert eng["restore_verify"] == "bit-exact" and c3["config"]["workload"] == B.WORKLOADS["c3"] and c3["dtype"].startswith("f32->bf16")
+
+
+def test_d2h_ceiling_control_flow(bench, monkeypatch, dist_1rank):
+    """The PCIe-ceiling leg needs a GPU for its number, not for its control flow: the buffer is allocated under the affinity of
+    the GPU's NUMA node and the affinity is put back, every rank reaches both barriers, and a measurement that fails on this
+    rank comes back as "not measured" instead of taking the bench line down (or leaving the other ranks in a collective)."""
+    import os
+
+    B = bench
+    real_empty = torch.empty
+    seen = {}
+
+    def empty(*a, **k):
+        if k.get("device") is not None:
+            k["device"] = "cpu"
+        else:
+            seen["affinity_at_host_alloc"] = os.sched_getaffinity(0)
+        return real_empty(*a, **k)
+
+    monkeypatch.setattr(torch, "empty", empty)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    before = os.sched_getaffinity(0)
+    one = sorted(before)[0]
+    monkeypatch.setattr(B, "_numa_cpus_of_gpu", lambda idx: [one])
+    dev = torch.device("cuda", 0)
+    out = _ceiling_with_small_buffers(B, dev)
+    assert seen["affinity_at_host_alloc"] == {one} and os.sched_getaffinity(0) == before
+    assert out["per_gpu_min_GBps"] > 0 and out["per_gpu_max_GBps"] >= out["per_gpu_min_GBps"] and "NUMA" in out["what"] and "unbound" not in out["what"]
+    # node unknown: measured unbound, and said so
+    monkeypatch.setattr(B, "_numa_cpus_of_gpu", lambda idx: None)
+    out = _ceiling_with_small_buffers(B, dev)
+    assert out["per_gpu_min_GBps"] > 0 and "unbound" in out["what"] and os.sched_getaffinity(0) == before
+    # the allocation fails on this rank: both barriers are still reached, the result says why there is no number
+    def broken(*a, **k):
+        raise RuntimeError("out of pinned memory")
+
+    monkeypatch.setattr(torch.Tensor, "pin_memory", broken)
+    monkeypatch.setattr(B, "_numa_cpus_of_gpu", lambda idx: [one])
+    barriers = []
+    real_barrier = B.dist.barrier
+    monkeypatch.setattr(B.dist, "barrier", lambda *a, **k: (barriers.append(1), real_barrier(*a, **k))[1])
+    out = _ceiling_with_small_buffers(B, dev)
+    assert out["per_gpu_min_GBps"] is None and "out of pinned memory" in out["what"] and len(barriers) == 2
+    assert os.sched_getaffinity(0) == before
+
+
+def _ceiling_with_small_buffers(B, dev):
+    class Tiny(int):  # d2h_ceiling computes ``gib << 30`` bytes: 4 KiB instead of GiBs here
+        def __lshift__(self, n):
+            return 4096
+
+    return B.d2h_ceiling(dev, 1, gib=Tiny(1), reps=2)
+
+
+def test_numa_cpus_of_gpu_reads_sysfs(bench, monkeypatch, tmp_path):
+    """PCI address from the device properties -> numa_node -> cpulist ("0-3,8-9"); anything missing means "unknown"."""
+    import builtins
+
+    B = bench
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1B, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    files = {"/sys/bus/pci/devices/0000:1b:00.0/numa_node": "1\n", "/sys/devices/system/node/node1/cpulist": "0-3,8-9,12\n"}
+    real_open = builtins.open
+
+    def fake_open(path, *a, **k):
+        if str(path) in files:
+            p = tmp_path / str(path).strip("/").replace("/", "_")
+            p.write_text(files[str(path)])
+            return real_open(p, *a, **k)
+        if str(path).startswith("/sys/"):
+            raise FileNotFoundError(path)
+        return real_open(path, *a, **k)
+
+    monkeypatch.setattr(builtins, "open", fake_open)
+    assert B._numa_cpus_of_gpu(0) == [0, 1, 2, 3, 8, 9, 12]
+    files["/sys/bus/pci/devices/0000:1b:00.0/numa_node"] = "-1\n"
+    assert B._numa_cpus_of_gpu(0) is None
+    props.pci_bus_id = 0x2C  # no such device in sysfs
+    assert B._numa_cpus_of_gpu(0) is None
