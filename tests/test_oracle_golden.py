@@ -227,3 +227,60 @@ def test_pack_scatter_oracle_roundtrip():
     assert bit_equal(back[0], ts[0].to(torch.bfloat16).to(torch.float32)) and bit_equal(back[1], ts[1])
     shard, bounds = orc.shard_bounds(10_000, 8)
     assert shard == 1536 and bounds[0] == (0, 1536) and bounds[-1][1] == 10_000 and bounds[6] == (9216, 10_000)
+
+
+def test_utils_diff_matches_reference():
+    """``checkpointing.utils.diff`` (reference utils.py:124-182, what the reference's own tests compare state dicts with):
+    same only-left / only-right / mismatch reports, same exception where the reference raises."""
+    from _diff_cases import cases, normal
+
+    from nvidia_resiliency_ext.checkpointing.utils import diff
+
+    golden = json.load(open(GOLDEN / "utils_diff.json"))
+    assert set(golden) == set(cases())
+    for name, (left, right) in cases().items():
+        want = golden[name]
+        if "raises" in want:
+            with pytest.raises(Exception) as err:
+                diff(left, right)
+            assert type(err.value).__name__ == want["raises"], name
+        else:
+            assert normal(diff(left, right)) == want, name
+
+
+def test_logging_helpers_and_wrap_for_async_behave_like_the_reference(caplog):
+    """reference utils.py:35-82,102-120: ``debug_time`` logs "<scope path> took <s>s" (DEBUG, or WARNING once a threshold is
+    given and reached), scopes nest with ".", ``debug_msg`` prefixes the scope path, ``wrap_for_async`` runs the function with
+    the collector off and turns it back on."""
+    import gc
+    import logging
+
+    from nvidia_resiliency_ext.checkpointing.utils import debug_msg, debug_time, wrap_for_async
+
+    log = logging.getLogger("nvrx.test.scope")
+    with caplog.at_level(logging.DEBUG, logger="nvrx.test.scope"):
+        with debug_time("outer", log):
+            with debug_time("inner"):
+                debug_msg("hello")
+            with debug_time("quick", threshold=60.0):
+                pass
+            with debug_time("slow", threshold=0.0):
+                pass
+    got = [(r.levelno, r.getMessage()) for r in caplog.records if r.name == "nvrx.test.scope"]
+    assert (logging.DEBUG, "outer.inner hello") in got
+    assert any(lvl == logging.DEBUG and msg.startswith("outer.inner took ") and msg.endswith("s") for lvl, msg in got)
+    assert not any("outer.quick" in msg for _, msg in got)
+    assert any(lvl == logging.WARNING and msg.startswith("outer.slow took ") for lvl, msg in got)
+    assert any(lvl == logging.DEBUG and msg.startswith("outer took ") for lvl, msg in got)
+
+    seen = []
+    wrapped = wrap_for_async(lambda sd, path, flag=False: seen.append((gc.isenabled(), sd, path, flag)))
+    assert gc.isenabled()
+    assert wrapped({"a": 1}, "p", flag=True) is None
+    assert seen == [(False, {"a": 1}, "p", True)] and gc.isenabled()
+    gc.disable()
+    try:
+        wrapped({}, "q")
+        assert not gc.isenabled()  # it was off before: stays off
+    finally:
+        gc.enable()
