@@ -20,7 +20,7 @@ os.environ["PYTHONPATH"] = os.pathsep.join([str(PKG_ROOT), str(ROOT), os.environ
 
 GOLDEN = ROOT / "tests" / "golden"
 
-# the reference's own unit tests (verbatim fixtures) are run by tests/test_gpu_reference_suite.py under torchrun, not collected here
+# the reference's own unit tests (verbatim fixtures) are run by tests/test_gpu_zzz_reference_suite.py under torchrun, not collected here
 collect_ignore_glob = ["golden/ref_tests/*"]
 
 

@@ -1,5 +1,5 @@
 """Copies the reference's OWN unit tests for the hot path into tests/golden/ref_tests/ (test fixtures, category (b)): they are
-executed -- unmodified -- against this repo's mirror of the API by tests/test_gpu_reference_suite.py on the GPU box, where
+executed -- unmodified -- against this repo's mirror of the API by tests/test_gpu_zzz_reference_suite.py on the GPU box, where
 /root/reference does not exist.  Run in the build container: ``python tests/golden/make_ref_tests.py``.
 
 Files (reference tests/checkpointing/unit/): __init__.py (TempNamedDir), conftest.py, test_utilities.py, test_async_save.py,

@@ -537,7 +537,7 @@ from test_ptl_glue_cpu import glue  # noqa: E402,F401  (fixture: stub of the thr
 
 
 def test_ptl_glue_drives_the_local_manager(glue, monkeypatch, built_library, shm_dir, dist_1rank):  # noqa: F811
-    """CPU twin of tests/test_gpu_api.py::test_ptl_glue_drives_the_local_manager_on_gpu (same flow on the stand-in device)."""
+    """CPU twin of tests/test_gpu_zzy_ptl_glue.py::test_ptl_glue_drives_the_local_manager_on_gpu (same flow on the stand-in device)."""
     from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
     from nvidia_resiliency_ext.checkpointing.local.basic_state_dict import BasicTensorAwareStateDict
     from nvidia_resiliency_ext.checkpointing.local.ckpt_managers.local_manager import LocalCheckpointManager

@@ -1,11 +1,11 @@
-"""The torchrun runner of the reference's own unit tests (tests/test_gpu_reference_suite.py) itself, on CPU: results come back
+"""The torchrun runner of the reference's own unit tests (tests/test_gpu_zzz_reference_suite.py) itself, on CPU: results come back
 through files, a process a test leaves behind neither blocks the call nor survives it, a time limit ends in an assertion."""
 import os
 import time
 
 import pytest
 
-import test_gpu_reference_suite as rs
+import test_gpu_zzz_reference_suite as rs
 
 
 def _fixture_tree(root, body):
