@@ -2,7 +2,7 @@
 set -u
 O=gpurun_out/v2b; mkdir -p $O
 make -C nvidia-resiliency-ext_b200/csrc -j8 > $O/build.log 2>&1 || { tail -20 $O/build.log; exit 1; }
-NVRX_B200_TEST_UNVALIDATED=1 timeout 1500 python -m pytest tests/test_gpu_api.py tests/test_gpu_zzero_copy.py tests/test_gpu_zcrc.py tests/test_gpu_reference_suite.py -m gpu -q --timeout=900 > $O/pytest_refix.log 2>&1
+NVRX_B200_TEST_UNVALIDATED=1 timeout 1500 python -m pytest tests/test_gpu_api.py tests/test_gpu_zzero_copy.py tests/test_gpu_zcrc.py tests/test_gpu_zzz_reference_suite.py -m gpu -q --timeout=900 > $O/pytest_refix.log 2>&1
 tail -12 $O/pytest_refix.log | cut -c1-300
 timeout 600 python tools/restore_breakdown.py > $O/restore_breakdown.json 2> $O/restore_breakdown.err; tail -3 $O/restore_breakdown.err | cut -c1-300; cat $O/restore_breakdown.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk_ -c 80 --csv --log-file $O/launches.csv \
