@@ -48,16 +48,21 @@ class CheckpointMetadataCache:
     def get_cache_metadata(self):
         return self.cached_central_plan, self.cached_local_plan, self.validated_cache_reuse, self.loaded_all_plans
 
-    def set_cache_metadata(self, central_plan: SavePlan, local_plan: SavePlan, unchanged: bool, loaded_reuse: bool = False):
-        self.validated_loaded_metadata_reuse = loaded_reuse
+    def set_cache_metadata(self, central_plan: SavePlan, local_plan: SavePlan, global_md_verify_reuse: bool, *, unchanged: Optional[bool] = None):
+        """Store the plans of this save.  ``global_md_verify_reuse``: the plans stored in the loaded checkpoint still match
+        (reference state_dict_saver.py:115-133).  ``unchanged`` (added, optional): the all-ranks verdict that the local plans
+        equal the cached ones; without it the central plans are compared like the reference does."""
+        if unchanged is None:
+            unchanged = bool(central_plan == self.cached_central_plan)
+        self.validated_loaded_metadata_reuse = global_md_verify_reuse
         self.validated_cache_reuse = unchanged and self.cached_central_plan is not None
         self.cached_central_plan = central_plan
         self.cached_local_plan = local_plan
 
-    def prepare_save_state_dict_ret(self, rank: int, coordinator_rank: int, ret: Tuple) -> Tuple:
+    def prepare_save_state_dict_ret(self, rank: int, coordinator: int, save_state_dict_ret: Tuple) -> Tuple:
         """On the coordinator keep the freshest global metadata and substitute the cached one when planning was skipped."""
-        writer, metadata, dist_wrapper = ret
-        if rank == coordinator_rank:
+        writer, metadata, dist_wrapper = save_state_dict_ret
+        if rank == coordinator:
             if metadata is None:  # planning was skipped (cached plan) or needed no metadata exchange (loaded plans match)
                 metadata = self.cached_global_metadata
             else:
@@ -174,7 +179,7 @@ def save_state_dict_async_plan(
     logger.debug(f"rank: {rank}, write(async) time: {time() - t1}")
     ret = (storage_writer, global_metadata, dist_wrapper)
     if cache is not None:
-        cache.set_cache_metadata(central_plan, local_plan, unchanged, loaded_reuse)
+        cache.set_cache_metadata(central_plan, local_plan, loaded_reuse, unchanged=unchanged)
         ret = cache.prepare_save_state_dict_ret(rank, coordinator_rank, ret)
     return ret
 
