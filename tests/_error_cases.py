@@ -31,6 +31,15 @@ def _plain(x):
     return f"<{type(x).__name__}>"
 
 
+def _write_text(path, text):
+    with open(path, "w") as fh:
+        fh.write(text)
+
+
+def _raise_value_error(msg):
+    raise ValueError(msg)
+
+
 def scenarios(tmp):
     """name -> outcome.  Imports happen inside: the caller decides which ``nvidia_resiliency_ext`` is on sys.path."""
     import torch
@@ -144,6 +153,36 @@ def scenarios(tmp):
         return seen
 
     out["async_request_finalize_fns_keep_order"] = _outcome(finalize_order)
+
+    # ---- AsyncCallsQueue with a persistent worker (host functions only) -----------------------------------------------
+    from nvidia_resiliency_ext.checkpointing.async_ckpt.core import AsyncCallsQueue
+
+    def queue_flow():
+        d = fresh()
+        q = AsyncCallsQueue(persistent=True, cpu_shm_mode=True)  # (the reference worker needs no CUDA device in this mode)
+        seen = []
+        try:
+            idx0 = q.schedule_async_request(AsyncRequest(_write_text, (os.path.join(d, "a.txt"), "A"), [lambda: seen.append("fin0")]))
+            idx1 = q.schedule_async_request(AsyncRequest(_write_text, (os.path.join(d, "b.txt"), "B"), [lambda: seen.append("fin1")]))
+            pending = q.get_num_unfinalized_calls()
+            done = q.maybe_finalize_async_calls(blocking=True, no_dist=True)
+            left = q.get_num_unfinalized_calls()
+            again = q.maybe_finalize_async_calls(blocking=True, no_dist=True)
+            files = sorted((f, open(os.path.join(d, f)).read()) for f in os.listdir(d))
+            return idx0, idx1, pending, done, left, again, seen, files
+        finally:
+            q.close()
+
+    out["queue_two_requests_finalize_in_order"] = _outcome(queue_flow)
+
+    def queue_sync_request():
+        d = fresh()
+        seen = []
+        r = AsyncRequest(_write_text, (os.path.join(d, "s.txt"), "S"), [lambda: seen.append("fin")])
+        r.execute_sync()
+        return seen, open(os.path.join(d, "s.txt")).read()
+
+    out["request_execute_sync_runs_fn_and_finalizers"] = _outcome(queue_sync_request)
 
     # ---- parse_group_sequence ----------------------------------------------------------------------------------------
     for name, kw in {

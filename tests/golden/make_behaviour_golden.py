@@ -10,23 +10,24 @@ import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src"
-assert os.path.isdir(REF_SRC), "the reference tree is needed to (re)generate golden vectors"
-sys.path.insert(0, REF_SRC)
+sys.path.insert(0, REF_SRC)  # (also in the spawned checkpoint worker, which imports this file as its main module)
 sys.path.insert(0, os.path.dirname(HERE))
 
-import torch.distributed as dist  # noqa: E402
+if __name__ == "__main__":
+    assert os.path.isdir(REF_SRC), "the reference tree is needed to (re)generate golden vectors"
+    import torch.distributed as dist
 
-import nvidia_resiliency_ext  # noqa: E402
+    import nvidia_resiliency_ext
 
-assert nvidia_resiliency_ext.__file__.startswith(REF_SRC), nvidia_resiliency_ext.__file__
-from _error_cases import scenarios  # noqa: E402
+    assert nvidia_resiliency_ext.__file__.startswith(REF_SRC), nvidia_resiliency_ext.__file__
+    from _error_cases import scenarios
 
-os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-os.environ.setdefault("MASTER_PORT", "29671")
-dist.init_process_group("gloo", rank=0, world_size=1)
-with tempfile.TemporaryDirectory() as tmp:
-    out = scenarios(tmp)
-dist.destroy_process_group()
-with open(os.path.join(HERE, "behaviour.json"), "w") as fh:
-    json.dump(out, fh, indent=1, sort_keys=True)
-print(json.dumps(out, indent=1))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29671")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    with tempfile.TemporaryDirectory() as tmp:
+        out = scenarios(tmp)
+    dist.destroy_process_group()
+    with open(os.path.join(HERE, "behaviour.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print(json.dumps(out, indent=1))
