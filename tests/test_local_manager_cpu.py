@@ -242,3 +242,31 @@ def test_saving_does_not_switch_off_the_trainers_zip_checksums(tmp_path, dist_1r
     except RuntimeError:
         pass
     assert torch.serialization.get_crc32_options() is True
+
+
+def _w_replicated_flow(rank, world, base):
+    import json
+
+    from _replicated_manager_flow import run
+
+    got = run(rank, os.path.join(base, "nodes"))
+    with open(os.path.join(base, f"rank{rank}.json"), "w") as fh:
+        json.dump(got, fh)
+
+
+def test_replicated_manager_flow_matches_the_reference(tmp_path):
+    """4 gloo ranks, three clique layouts: files on every node after a replicated save, find_latest and what load() returns
+    after one node lost its directory (retrieve_plan + execute_plan), files after the next save (cleanup) -- all equal to what
+    the imported reference did in the same flow (tests/golden/replicated_manager_4rank.json, generated by
+    tests/golden/make_replicated_manager_golden.py; flow in tests/_replicated_manager_flow.py)."""
+    from _replicated_manager_flow import WORLD
+
+    run_ranks(_w_replicated_flow, WORLD, str(tmp_path), timeout=300.0)
+    golden = json.load(open(GOLDEN / "replicated_manager_4rank.json"))
+    for rank in range(WORLD):
+        got = json.load(open(tmp_path / f"rank{rank}.json"))
+        want = golden[str(rank)]
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g == w, f"rank {rank}, scenario {w['scenario']}:\n mirror    {g}\n reference {w}"
+            assert g["loaded_tensors"] == g["expected_tensors"]
