@@ -136,6 +136,43 @@ def scenarios(tmp):
 
     out["manager_keeps_only_the_latest_iteration"] = _outcome(keeps_only_latest)
 
+    def older_iteration():
+        mgr = LocalCheckpointManager(fresh())
+        mgr.save(tasd(), 5, is_async=False)
+        mgr.find_latest()  # (latest_iteration is invalid right after a save: this makes 5 known)
+        return mgr.save(tasd(), 3, is_async=False)
+
+    out["manager_refuses_an_older_iteration"] = _outcome(older_iteration)
+
+    def dirty_file():
+        mgr = LocalCheckpointManager(fresh())
+        mgr._ensure_dir()
+        mgr._local_ckpt_path_from_id(mgr._ckpt_id(3), True).touch()
+        return mgr.save(tasd(), 3, is_async=False)
+
+    out["manager_dirty_file_of_the_same_id"] = _outcome(dirty_file)
+
+    def dirty_is_invisible_and_cleaned():
+        mgr = LocalCheckpointManager(fresh())
+        mgr._ensure_dir()
+        dirty = mgr._local_ckpt_path_from_id(mgr._ckpt_id(3), True)
+        dirty.touch()
+        seen = (dirty.name, mgr.find_latest())
+        mgr._cleanup_failed_save(3)
+        return seen, sorted(p.name for p in mgr.local_ckpt_dir.iterdir())
+
+    out["manager_dirty_files_are_invisible_and_removed"] = _outcome(dirty_is_invisible_and_cleaned)
+
+    def load_after_file_vanished():
+        mgr = LocalCheckpointManager(fresh())
+        mgr.save(tasd(), 4, is_async=False)
+        mgr.find_latest()
+        for p in mgr.local_ckpt_dir.iterdir():
+            p.unlink()
+        return mgr.load()
+
+    out["manager_load_after_the_file_vanished"] = _outcome(load_after_file_vanished)
+
     # ---- AsyncRequest ------------------------------------------------------------------------------------------------
     def frozen():
         r = AsyncRequest(print, ("x",), [])
