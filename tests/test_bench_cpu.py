@@ -213,3 +213,64 @@ def test_numa_cpus_of_gpu_reads_sysfs(bench, monkeypatch, tmp_path):
     assert B._numa_cpus_of_gpu(0) is None
     props.pci_bus_id = 0x2C  # no such device in sysfs
     assert B._numa_cpus_of_gpu(0) is None
+
+
+def _w_run_arm_two_ranks(rank, world, out_dir):
+    """One rank of a two-rank ``run_arm`` (engine arm, every leg the driver's N>1 runs execute except the GEMM loop and the
+    PCIe ceiling) on the stand-in device with gloo collectives."""
+    import json
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    import bench as B
+
+    mp_ = pytest.MonkeyPatch()
+
+    def over(op):
+        def reduce(x):
+            t = torch.tensor([float(x)], dtype=torch.float64)
+            dist.all_reduce(t, op=op)
+            return t.item()
+
+        return reduce
+
+    try:
+        mp_.setattr(B, "max_over_ranks", over(dist.ReduceOp.MAX))
+        mp_.setattr(B, "min_over_ranks", over(dist.ReduceOp.MIN))
+        mp_.setattr(torch.cuda, "Event", _Event)
+        mp_.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+        mp_.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None))
+        mp_.setattr(B, "ClockSampler", lambda idx: types.SimpleNamespace(__enter__=lambda: None, __exit__=lambda *a: None, summary=lambda: {"sm_mhz": None}))
+        with fake_device(mp_) as (engine, lib):
+            def state(dev, seed=0, scale=1.0):
+                g = torch.Generator().manual_seed(seed)  # (the bench seeds every rank differently: 1234 + rank)
+                sd = {"model": {f"l{i}": FakeCudaTensor.wrap(torch.randn(65 + i, 33, generator=g)) for i in range(4)},
+                      "optimizer": {"state": {i: {"exp_avg": FakeCudaTensor.wrap(torch.randn(65 + i, 33, generator=g)),
+                                                  "step": FakeCudaTensor.wrap(torch.tensor(float(i)))} for i in range(4)}}}
+                return sd, sum(t.numel() * t.element_size() for t in B.flatten(sd))
+
+            mp_.setattr(B, "llama3_8b_shard_state", state)
+            line = B.run_arm(_args(B), rank, world, 0)
+        with open(f"{out_dir}/line{rank}.json", "w") as fh:
+            json.dump(line, fh)
+    finally:
+        mp_.undo()
+
+
+def test_run_arm_on_two_ranks(tmp_path, built_library):
+    """The driver launches bench.py on 2, 4 and 8 ranks: every collective of run_arm (barriers of the loops, max / min over
+    ranks, the local manager's find_latest gathers with ONE session id for all ranks) must line up across ranks.  Executed here
+    on two gloo ranks with the stand-in device; both ranks assemble the same whole-job line."""
+    import json
+
+    from _mp import run_ranks
+
+    run_ranks(_w_run_arm_two_ranks, 2, str(tmp_path), timeout=300.0)
+    lines = [json.load(open(tmp_path / f"line{r}.json")) for r in range(2)]
+    for line in lines:
+        assert line["n_gpus"] == 2 and line["verify"] in ("bit-exact", "skipped") and line["restore_verify"] == "bit-exact"
+        assert line["local_save_stall_ms"] >= 0 and line["restore_s"] > 0 and line["gpu_launches"] > 0
+    assert lines[0]["verify"] == "bit-exact"  # (rank 0 checks its file)
+    for key in ("value", "ms_per_step", "stall_ms", "restore_s", "local_save_persist_s", "config"):
+        assert lines[0][key] == lines[1][key], key  # max over ranks: the same number on every rank
