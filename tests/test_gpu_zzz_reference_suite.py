@@ -82,18 +82,17 @@ def worlds():
     return [w for w in (1, 2) if w <= n]
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_reference_async_save_tests(world):
+def _needs(world):
     if world not in worlds():
         pytest.skip(f"needs >= {world} CUDA devices")
+
+
+def _async_save_tests(world):
     out = run_reference_tests(["test_async_save.py"], world, retries=1)
     assert "3 passed" in out
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_reference_local_checkpoint_tests(world):
-    if world not in worlds():
-        pytest.skip(f"needs >= {world} CUDA devices")
+def _local_checkpoint_tests(world):
     # test_find_latest_repl_disable asserts world_size >= 2 itself
     extra = ["-k", "not test_find_latest_repl_disable"] if world == 1 else []
     out = run_reference_tests(["test_basic_local.py", "test_cleanup.py"], world, extra, retries=1)
@@ -104,19 +103,46 @@ DCP_GROUPS = ["test_async_is_equivalent_to_sync", "test_invalid_async_setup", "t
               "test_cached_data_structure", "test_cpu_shm_for_gpu_tensors", "test_async_cp_with_multiple_queue_and_abort"]
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_reference_dcp_async_writer_tests(world):
+def _dcp_async_writer_tests(world):
     """All 13 cases of the reference's test_async_writer.py (the last -k pattern also selects ..._followed_by_delete).  Each
     group runs in a process of its own with its own time limit: in one process the file did not finish within 900 s on the
     B200 box in round 2 -- its last output came about 31 s in, then nothing.  Cause not found: every group passes on its own
     (profiles/r02_reference_dcp_tests.log), and the same 13 scenarios replayed in ONE process on the stand-in device
     (queues with daemon / non-daemon workers, failing writers, caches, abort + resume) finish, so the host logic alone does
     not hang."""
-    if world not in worlds():
-        pytest.skip(f"needs >= {world} CUDA devices")
     passed = 0
     for group in DCP_GROUPS:
         out = run_reference_tests(["test_async_writer.py"], world, ["-k", group], timeout=300, retries=1)
         assert " passed" in out and "failed" not in out, group
         passed += passed_count(out)
     assert passed == 13
+
+
+# one rank first (what a 1-GPU box runs; all green on B200 in round 2), the two-rank variants after them
+def test_reference_async_save_tests():
+    _async_save_tests(1)
+
+
+def test_reference_local_checkpoint_tests():
+    _local_checkpoint_tests(1)
+
+
+def test_reference_dcp_async_writer_tests():
+    _dcp_async_writer_tests(1)
+
+
+def test_reference_local_checkpoint_tests_two_ranks():
+    _needs(2)
+    _local_checkpoint_tests(2)
+
+
+def test_reference_async_save_tests_two_ranks():
+    """Both ranks save the SAME path in this file (test_async_save.py:38): at two ranks it found the writer that truncated the
+    file under the other rank's mapping (fixed: private name + rename); not repeated on GPUs since."""
+    _needs(2)
+    _async_save_tests(2)
+
+
+def test_reference_dcp_async_writer_tests_two_ranks():
+    _needs(2)
+    _dcp_async_writer_tests(2)
