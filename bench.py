@@ -625,7 +625,15 @@ def run_arm(args, rank, world, local):
         del loop
     arm.close()
     shutil.rmtree(out_dir, ignore_errors=True)
-    local_leg = {} if args.no_restore else local_manager_leg(args.impl, sd, tensors, total, rank, args.narrow)
+    local_leg = {}
+    if not args.no_restore:
+        try:
+            local_leg = local_manager_leg(args.impl, sd, tensors, total, rank, args.narrow)
+        except Exception as exc:  # noqa: BLE001 - the headline numbers above are measured: a failure here is reported in the line
+            import traceback
+
+            traceback.print_exc()
+            local_leg = {"local_leg_error": repr(exc)}
     ceiling = None if args.no_ceiling else d2h_ceiling(dev, world)
     if engine_arm:
         launches += engine.launches - launches_before

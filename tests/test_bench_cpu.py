@@ -274,3 +274,23 @@ def test_run_arm_on_two_ranks(tmp_path, built_library):
     assert lines[0]["verify"] == "bit-exact"  # (rank 0 checks its file)
     for key in ("value", "ms_per_step", "stall_ms", "restore_s", "local_save_persist_s", "config"):
         assert lines[0][key] == lines[1][key], key  # max over ranks: the same number on every rank
+
+
+def test_a_failing_local_leg_is_reported_inside_the_line(bench, monkeypatch, built_library, dist_1rank):
+    """The stall / e2e numbers are measured before the local-manager leg: an exception there (on every rank alike, e.g. the
+    session-id assertion of the first 2-GPU run) must not cost the whole line."""
+    import json
+
+    B = bench
+    monkeypatch.setattr(B, "ClockSampler", lambda idx: types.SimpleNamespace(__enter__=lambda: None, __exit__=lambda *a: None, summary=lambda: {"sm_mhz": None}))
+
+    def broken(*a, **k):
+        raise AssertionError("session == self.session_id")
+
+    monkeypatch.setattr(B, "local_manager_leg", broken)
+    with fake_device(monkeypatch) as (engine, lib):
+        monkeypatch.setattr(B, "llama3_8b_shard_state", lambda dev, seed=0, scale=1.0: (_small_state(), sum(t.numel() * t.element_size() for t in B.flatten(_small_state()))))
+        line = B.run_arm(_args(B, no_c3_kernel=True), 0, 1, 0)
+    json.dumps(line)
+    assert "session == self.session_id" in line["local_leg_error"] and line["restore_GBps"] is None
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["verify"] == "bit-exact" and line["roofline"]["algorithmic_bytes_per_launch"] > 0
