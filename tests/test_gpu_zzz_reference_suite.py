@@ -88,14 +88,14 @@ def _needs(world):
 
 
 def _async_save_tests(world):
-    out = run_reference_tests(["test_async_save.py"], world, retries=1)
+    out = run_reference_tests(["test_async_save.py"], world, timeout=240, retries=1)
     assert "3 passed" in out
 
 
 def _local_checkpoint_tests(world):
     # test_find_latest_repl_disable asserts world_size >= 2 itself
     extra = ["-k", "not test_find_latest_repl_disable"] if world == 1 else []
-    out = run_reference_tests(["test_basic_local.py", "test_cleanup.py"], world, extra, retries=1)
+    out = run_reference_tests(["test_basic_local.py", "test_cleanup.py"], world, extra, timeout=240, retries=1)
     assert " passed" in out and "failed" not in out
 
 
@@ -112,7 +112,7 @@ def _dcp_async_writer_tests(world):
     not hang."""
     passed = 0
     for group in DCP_GROUPS:
-        out = run_reference_tests(["test_async_writer.py"], world, ["-k", group], timeout=300, retries=1)
+        out = run_reference_tests(["test_async_writer.py"], world, ["-k", group], timeout=150, retries=1)
         assert " passed" in out and "failed" not in out, group
         passed += passed_count(out)
     assert passed == 13
