@@ -11,7 +11,7 @@ from hypothesis import strategies as st
 from oracle import crc_oracle as co
 from oracle import snapshot_oracle as orc
 
-SETTINGS = dict(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+SETTINGS = dict(max_examples=int(__import__("os").environ.get("NVRX_TEST_EXAMPLES", "30")), deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 sizes_strategy = st.lists(
     st.one_of(st.integers(0, 2048), st.integers(60_000, 70_000), st.integers(0, 300_000)), min_size=1, max_size=12
